@@ -1,0 +1,755 @@
+// extern "C" boundary of libhexl_b200.so (declared in include/hexl_b200.h).
+//
+// Host-side responsibilities, all one-off or O(1) per call:
+//   * argument validation mirroring the reference's HEXL_CHECKs,
+//   * NTT handle = (N, q, root) -> twiddle tables, built on the host exactly as
+//     hexl/ntt/ntt-internal.cpp:54-169 defines them, uploaded once per device,
+//   * pointer classification: device pointers are launched on in place and
+//     asynchronously; host pointers are staged through the GPU in pipelined
+//     chunks (H2D / kernel / D2H on rotating streams) and, for batched calls,
+//     optionally split across several GPUs with no inter-GPU traffic.
+// There is no CPU compute path here: without a CUDA device every compute entry
+// point returns HEXL_B200_ERR_NO_DEVICE.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hexl_b200.h"
+#include "internal.h"
+#include "numtheory.h"
+
+using namespace hexl_b200;
+
+namespace hexl_b200 {
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+uint64_t launches_so_far() { return g_launches.load(std::memory_order_relaxed); }
+}  // namespace hexl_b200
+
+// ------------------------------------------------------------------ handle type
+struct hexl_b200_ntt {
+  std::atomic<int> refs{1};
+  uint64_t n = 0, q = 0, root = 0;
+  int log_n = 0;
+  // reference layouts (host), returned by hexl_b200_ntt_table
+  std::vector<uint64_t> w, w_precon, inv_seq, inv_seq_precon;
+  // tree layouts for the device: node k -> {value, Shoup factor}
+  std::vector<Twiddle> fwd_tree, inv_tree;
+  Twiddle inv_n{}, inv_n_w{};
+  std::mutex mu;
+  struct Dev {
+    Twiddle* fwd = nullptr;
+    Twiddle* inv = nullptr;
+  };
+  std::map<int, Dev> dev;  // device ordinal -> uploaded tables
+};
+
+namespace {
+
+thread_local std::string t_error;
+std::atomic<int> g_debug{0};
+std::mutex g_cfg_mu;
+std::vector<int> g_host_devices;  // empty = current device only
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  t_error = buf;
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
+    return fail(HEXL_B200_ERR_NO_DEVICE, "%s: no usable CUDA device (%s)", what, cudaGetErrorString(e));
+  return fail(HEXL_B200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CU(call)                                         \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+// ------------------------------------------------------------- pointer kinds
+enum class Where { Host, Device };
+struct PtrInfo {
+  Where where;
+  int device;  // valid for Device
+};
+
+int classify(const void* p, PtrInfo* out) {
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return cuda_fail(e, "cudaPointerGetAttributes");
+  }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
+    out->where = Where::Device;
+    out->device = a.device;
+  } else {
+    out->where = Where::Host;
+    out->device = -1;
+  }
+  return 0;
+}
+
+// All non-null pointers of a call must live in the same place.
+int classify_all(std::initializer_list<const void*> ptrs, PtrInfo* out) {
+  bool have = false;
+  for (const void* p : ptrs) {
+    if (!p) continue;
+    PtrInfo pi;
+    int rc = classify(p, &pi);
+    if (rc) return rc;
+    if (!have) {
+      *out = pi;
+      have = true;
+    } else if (pi.where != out->where || (pi.where == Where::Device && pi.device != out->device)) {
+      return fail(HEXL_B200_ERR_MIXED_POINTERS, "host and device pointers (or two devices) mixed in one call");
+    }
+  }
+  return 0;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  int enter(int dev) {
+    CU(cudaGetDevice(&prev));
+    if (prev != dev) {
+      CU(cudaSetDevice(dev));
+      switched = true;
+    }
+    return 0;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+// ----------------------------------------------------------- host-pointer staging
+// One staging context per device: kSlots rotating {stream, device buffers}.
+constexpr int kSlots = 3;
+constexpr size_t kChunkBytes = 32u << 20;  // per buffer per slot
+
+struct StageCtx {
+  std::mutex mu;
+  cudaStream_t stream[kSlots] = {};
+  u64* buf[kSlots][3] = {};  // [slot][result/in-place a, b, c]
+  size_t cap[kSlots][3] = {};
+  bool ready = false;
+  int init() {
+    if (ready) return 0;
+    for (int s = 0; s < kSlots; ++s) CU(cudaStreamCreateWithFlags(&stream[s], cudaStreamNonBlocking));
+    ready = true;
+    return 0;
+  }
+  int reserve(int slot, int which, size_t bytes) {
+    if (cap[slot][which] >= bytes) return 0;
+    if (buf[slot][which]) CU(cudaFree(buf[slot][which]));
+    buf[slot][which] = nullptr;
+    cap[slot][which] = 0;
+    CU(cudaMalloc(&buf[slot][which], bytes));
+    cap[slot][which] = bytes;
+    return 0;
+  }
+};
+
+std::mutex g_stage_mu;
+std::map<int, StageCtx*> g_stage;
+
+StageCtx* stage_for(int dev) {
+  std::lock_guard<std::mutex> lk(g_stage_mu);
+  auto it = g_stage.find(dev);
+  if (it == g_stage.end()) it = g_stage.emplace(dev, new StageCtx()).first;
+  return it->second;
+}
+
+// A host-pointer job: `total` elements, processed in chunks that are multiples
+// of `unit` elements.  a is always present; b optional; result may alias a or b.
+// launch(dev_result, dev_a, dev_b, elems, stream) enqueues the kernel(s).
+template <class Launch>
+int run_host_on_device(int dev, u64* result, const u64* a, const u64* b, u64 total, u64 unit,
+                       Launch&& launch, bool wait) {
+  DeviceGuard g;
+  if (int rc = g.enter(dev)) return rc;
+  StageCtx* st = stage_for(dev);
+  std::lock_guard<std::mutex> lk(st->mu);
+  if (int rc = st->init()) return rc;
+  u64 chunk = (kChunkBytes / sizeof(u64)) / unit * unit;
+  if (chunk == 0) chunk = unit;
+  int slot = 0;
+  for (u64 off = 0; off < total; off += chunk, slot = (slot + 1) % kSlots) {
+    const u64 elems = (total - off < chunk) ? total - off : chunk;
+    const size_t bytes = elems * sizeof(u64);
+    if (int rc = st->reserve(slot, 0, bytes)) return rc;
+    if (b)
+      if (int rc = st->reserve(slot, 1, bytes)) return rc;
+    cudaStream_t s = st->stream[slot];
+    CU(cudaMemcpyAsync(st->buf[slot][0], a + off, bytes, cudaMemcpyHostToDevice, s));
+    if (b) CU(cudaMemcpyAsync(st->buf[slot][1], b + off, bytes, cudaMemcpyHostToDevice, s));
+    cudaError_t e = launch(st->buf[slot][0], st->buf[slot][0], b ? st->buf[slot][1] : nullptr, elems, s);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    CU(cudaMemcpyAsync(result + off, st->buf[slot][0], bytes, cudaMemcpyDeviceToHost, s));
+  }
+  if (wait)
+    for (int s = 0; s < kSlots; ++s) CU(cudaStreamSynchronize(st->stream[s]));
+  return 0;
+}
+
+int sync_stage(int dev) {
+  DeviceGuard g;
+  if (int rc = g.enter(dev)) return rc;
+  StageCtx* st = stage_for(dev);
+  std::lock_guard<std::mutex> lk(st->mu);
+  if (!st->ready) return 0;
+  for (int s = 0; s < kSlots; ++s) CU(cudaStreamSynchronize(st->stream[s]));
+  return 0;
+}
+
+std::vector<int> host_devices() {
+  std::lock_guard<std::mutex> lk(g_cfg_mu);
+  return g_host_devices;
+}
+
+// Split a host-pointer job over the configured devices by contiguous blocks of
+// whole units (no inter-GPU traffic), enqueue everything, then wait.
+template <class MakeLaunch>
+int run_host(u64* result, const u64* a, const u64* b, u64 total, u64 unit, MakeLaunch&& make) {
+  std::vector<int> devs = host_devices();
+  if (devs.empty() || total / unit < 2) {
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    if (!devs.empty()) cur = devs[0];
+    auto launch = make(cur);
+    if (!launch.ok) return launch.rc;
+    return run_host_on_device(cur, result, a, b, total, unit, launch, true);
+  }
+  const u64 units = total / unit;
+  const u64 ndev = devs.size() < units ? devs.size() : units;
+  int rc = 0;
+  for (u64 d = 0; d < ndev && !rc; ++d) {
+    const u64 lo = units * d / ndev * unit, hi = units * (d + 1) / ndev * unit;
+    auto launch = make(devs[d]);
+    if (!launch.ok) return launch.rc;
+    rc = run_host_on_device(devs[d], result + lo, a + lo, b ? b + lo : nullptr, hi - lo, unit, launch, false);
+  }
+  for (u64 d = 0; d < ndev; ++d) {
+    int rc2 = sync_stage(devs[d]);
+    if (!rc) rc = rc2;
+  }
+  return rc;
+}
+
+// ---------------------------------------------------------------- debug checks
+__global__ void bounds_kernel(const u64* p, u64 n, u64 bound, int* flag) {
+  u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (; i < n; i += stride) bad |= p[i] >= bound;
+  if (bad) atomicExch(flag, 1);
+}
+
+// HEXL_CHECK_BOUNDS analogue (check.hpp:33-36): every element < bound
+int check_bounds(const u64* p, u64 n, u64 bound, const PtrInfo& pi, const char* what) {
+  if (!g_debug.load() || !p) return 0;
+  if (pi.where == Where::Host) {
+    for (u64 i = 0; i < n; ++i)
+      if (p[i] >= bound) return fail(HEXL_B200_ERR_INVALID_ARG, "%s: element %llu exceeds bound", what, (unsigned long long)i);
+    return 0;
+  }
+  DeviceGuard g;
+  if (int rc = g.enter(pi.device)) return rc;
+  int* flag = nullptr;
+  CU(cudaMalloc(&flag, sizeof(int)));
+  CU(cudaMemset(flag, 0, sizeof(int)));
+  bounds_kernel<<<296, 256>>>(p, n, bound, flag);
+  count_launch();
+  int h = 0;
+  cudaError_t e = cudaMemcpy(&h, flag, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(flag);
+  if (e != cudaSuccess) return cuda_fail(e, "bounds check");
+  if (h) return fail(HEXL_B200_ERR_INVALID_ARG, "%s: an element exceeds its bound", what);
+  return 0;
+}
+
+// --------------------------------------------------------------- NTT tables
+int floor_log2(uint64_t x) { return 63 - __builtin_clzll(x); }
+
+bool check_ntt_arguments(uint64_t degree, uint64_t q, const char** why) {
+  // NTT::CheckArguments, hexl/ntt/ntt-internal.cpp:171-186
+  if (degree < 2 || (degree & (degree - 1))) { *why = "degree is not a power of 2 (>= 2)"; return false; }
+  if (degree > (1ull << 20)) { *why = "degree should be at most 2^20"; return false; }
+  if (q > (1ull << 62)) { *why = "modulus should be at most 2^62"; return false; }
+  if (q % (2 * degree) != 1) { *why = "modulus mod 2n != 1"; return false; }
+  if (!nt::is_prime(q)) { *why = "modulus is not prime"; return false; }
+  return true;
+}
+
+Twiddle make_twiddle(uint64_t v, uint64_t q) { return Twiddle{v, nt::multiply_factor(v, 64, q)}; }
+
+// hexl/ntt/ntt-internal.cpp:54-169 restated: psi^i goes to slot bitrev(i); the
+// inverse powers are additionally listed in the order the reference's inverse
+// transform consumes them (m = N/2 groups first, ..., m = 1 last).
+void build_tables(hexl_b200_ntt* h) {
+  const uint64_t n = h->n, q = h->q;
+  h->w.assign(n, 0);
+  h->w_precon.assign(n, 0);
+  h->inv_seq.assign(n, 0);
+  h->inv_seq_precon.assign(n, 0);
+  h->fwd_tree.assign(n, Twiddle{0, 0});
+  h->inv_tree.assign(n, Twiddle{0, 0});
+  const uint64_t root_inv = nt::inverse_mod(h->root, q);
+  uint64_t pw = 1, ipw = 1;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint64_t slot = nt::reverse_bits(i, h->log_n);
+    h->fwd_tree[slot] = make_twiddle(pw, q);
+    h->inv_tree[slot] = make_twiddle(ipw, q);  // (psi^i)^-1 = (psi^-1)^i
+    pw = nt::mul_mod(pw, h->root, q);
+    ipw = nt::mul_mod(ipw, root_inv, q);
+  }
+  for (uint64_t k = 0; k < n; ++k) {
+    h->w[k] = h->fwd_tree[k].w;
+    h->w_precon[k] = h->fwd_tree[k].wp;
+  }
+  uint64_t pos = 0;
+  h->inv_seq[pos] = h->inv_tree[0].w;
+  h->inv_seq_precon[pos++] = h->inv_tree[0].wp;
+  for (uint64_t m = n >> 1; m > 0; m >>= 1)
+    for (uint64_t i = 0; i < m; ++i, ++pos) {
+      h->inv_seq[pos] = h->inv_tree[m + i].w;
+      h->inv_seq_precon[pos] = h->inv_tree[m + i].wp;
+    }
+  const uint64_t inv_n = nt::inverse_mod(n, q);
+  h->inv_n = make_twiddle(inv_n, q);
+  h->inv_n_w = make_twiddle(nt::mul_mod(inv_n, h->inv_tree[1].w, q), q);
+}
+
+int device_tables(hexl_b200_ntt* h, int dev, NttDeviceTables* out) {
+  std::lock_guard<std::mutex> lk(h->mu);
+  auto it = h->dev.find(dev);
+  if (it == h->dev.end()) {
+    hexl_b200_ntt::Dev d;
+    const size_t bytes = h->n * sizeof(Twiddle);
+    CU(cudaMalloc(&d.fwd, bytes));
+    CU(cudaMalloc(&d.inv, bytes));
+    CU(cudaMemcpy(d.fwd, h->fwd_tree.data(), bytes, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d.inv, h->inv_tree.data(), bytes, cudaMemcpyHostToDevice));
+    it = h->dev.emplace(dev, d).first;
+  }
+  out->fwd = it->second.fwd;
+  out->inv = it->second.inv;
+  out->n = h->n;
+  out->log_n = h->log_n;
+  out->q = h->q;
+  out->inv_n = h->inv_n;
+  out->inv_n_w = h->inv_n_w;
+  return 0;
+}
+
+int create_common(hexl_b200_ntt** out, uint64_t degree, uint64_t q, uint64_t root, bool have_root) {
+  if (!out) return fail(HEXL_B200_ERR_INVALID_ARG, "out == nullptr");
+  *out = nullptr;
+  const char* why = "";
+  if (!check_ntt_arguments(degree, q, &why)) return fail(HEXL_B200_ERR_INVALID_ARG, "NTT(%llu, %llu): %s",
+                                                         (unsigned long long)degree, (unsigned long long)q, why);
+  if (!have_root) root = nt::minimal_primitive_root(2 * degree, q);
+  if (!nt::is_primitive_root(root, 2 * degree, q))
+    return fail(HEXL_B200_ERR_INVALID_ARG, "%llu is not a primitive 2*%llu'th root of unity",
+                (unsigned long long)root, (unsigned long long)degree);
+  hexl_b200_ntt* h = new (std::nothrow) hexl_b200_ntt();
+  if (!h) return fail(HEXL_B200_ERR_ALLOC, "out of host memory");
+  h->n = degree;
+  h->q = q;
+  h->root = root;
+  h->log_n = floor_log2(degree);
+  build_tables(h);
+  *out = h;
+  return 0;
+}
+
+struct NttLaunch {
+  bool ok = true;
+  int rc = 0;
+  NttDeviceTables t{};
+  bool forward = true;
+  int in_mf = 1, out_mf = 1;
+  u64 n = 0;
+  cudaError_t operator()(u64* r, const u64* a, const u64*, u64 elems, cudaStream_t s) const {
+    return forward ? launch_ntt_forward(t, r, a, in_mf, out_mf, elems / n, s)
+                   : launch_ntt_inverse(t, r, a, in_mf, out_mf, elems / n, s);
+  }
+};
+
+int ntt_compute(bool forward, hexl_b200_ntt* h, uint64_t* result, const uint64_t* operand,
+                uint64_t in_mf, uint64_t out_mf, uint64_t batch, void* stream) {
+  // checks of ntt-internal.cpp:191-200 (forward) / :255-262 (inverse)
+  if (!h) return fail(HEXL_B200_ERR_INVALID_ARG, "ntt handle == nullptr");
+  if (!result) return fail(HEXL_B200_ERR_INVALID_ARG, "result == nullptr");
+  if (!operand) return fail(HEXL_B200_ERR_INVALID_ARG, "operand == nullptr");
+  if (forward) {
+    if (!(in_mf == 1 || in_mf == 2 || in_mf == 4))
+      return fail(HEXL_B200_ERR_INVALID_ARG, "input_mod_factor must be 1, 2 or 4; got %llu", (unsigned long long)in_mf);
+    if (!(out_mf == 1 || out_mf == 4))
+      return fail(HEXL_B200_ERR_INVALID_ARG, "output_mod_factor must be 1 or 4; got %llu", (unsigned long long)out_mf);
+  } else {
+    if (!(in_mf == 1 || in_mf == 2))
+      return fail(HEXL_B200_ERR_INVALID_ARG, "input_mod_factor must be 1 or 2; got %llu", (unsigned long long)in_mf);
+    if (!(out_mf == 1 || out_mf == 2))
+      return fail(HEXL_B200_ERR_INVALID_ARG, "output_mod_factor must be 1 or 2; got %llu", (unsigned long long)out_mf);
+  }
+  if (batch == 0) return 0;
+  PtrInfo pi;
+  if (int rc = classify_all({result, operand}, &pi)) return rc;
+  if (int rc = check_bounds(operand, batch * h->n, h->q * in_mf, pi, "operand")) return rc;
+  if (pi.where == Where::Device) {
+    DeviceGuard g;
+    if (int rc = g.enter(pi.device)) return rc;
+    NttDeviceTables t;
+    if (int rc = device_tables(h, pi.device, &t)) return rc;
+    cudaError_t e = forward ? launch_ntt_forward(t, result, operand, (int)in_mf, (int)out_mf, batch, (cudaStream_t)stream)
+                            : launch_ntt_inverse(t, result, operand, (int)in_mf, (int)out_mf, batch, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "NTT launch");
+    return 0;
+  }
+  return run_host(result, operand, nullptr, batch * h->n, h->n, [&](int dev) {
+    NttLaunch L;
+    L.forward = forward;
+    L.in_mf = (int)in_mf;
+    L.out_mf = (int)out_mf;
+    L.n = h->n;
+    DeviceGuard g;
+    int rc = g.enter(dev);
+    if (!rc) rc = device_tables(h, dev, &L.t);
+    if (rc) {
+      L.ok = false;
+      L.rc = rc;
+    }
+    return L;
+  });
+}
+
+// ------------------------------------------------------------------ eltwise
+struct EltLaunch {
+  bool ok = true;
+  int rc = 0;
+  EltOp op;
+  EltParams p;
+  cudaError_t operator()(u64* r, const u64* a, const u64* b, u64 elems, cudaStream_t s) const {
+    EltParams q = p;
+    q.result = r;
+    q.a = a;
+    q.b = b;
+    q.n = elems;
+    return launch_eltwise(op, q, s);
+  }
+};
+
+int eltwise_dispatch(EltOp op, EltParams p, void* stream) {
+  if (p.n == 0) return fail(HEXL_B200_ERR_INVALID_ARG, "Require n != 0");
+  PtrInfo pi;
+  if (int rc = classify_all({p.result, p.a, p.b}, &pi)) return rc;
+  if (pi.where == Where::Device) {
+    DeviceGuard g;
+    if (int rc = g.enter(pi.device)) return rc;
+    cudaError_t e = launch_eltwise(op, p, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "eltwise launch");
+    return 0;
+  }
+  return run_host(p.result, p.a, p.b, p.n, 1, [&](int) {
+    EltLaunch L;
+    L.op = op;
+    L.p = p;
+    return L;
+  });
+}
+
+#define REQUIRE(cond, ...) \
+  if (!(cond)) return fail(HEXL_B200_ERR_INVALID_ARG, __VA_ARGS__)
+
+int debug_bounds(const u64* p, u64 n, u64 bound, const char* what, std::initializer_list<const void*> all) {
+  if (!g_debug.load()) return 0;
+  PtrInfo pi;
+  if (int rc = classify_all(all, &pi)) return rc;
+  return check_bounds(p, n, bound, pi, what);
+}
+
+}  // namespace
+
+// =============================================================== extern "C"
+extern "C" {
+
+const char* hexl_b200_version(void) { return "hexl-b200 0.1 (sm_100a; API of intel/hexl 1.2.5)"; }
+const char* hexl_b200_last_error(void) { return t_error.c_str(); }
+
+int hexl_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int hexl_b200_set_host_devices(const int* devices, int count) {
+  int n = hexl_b200_device_count();
+  std::vector<int> v;
+  for (int i = 0; i < count; ++i) {
+    if (!devices || devices[i] < 0 || devices[i] >= n)
+      return fail(HEXL_B200_ERR_INVALID_ARG, "device ordinal out of range");
+    v.push_back(devices[i]);
+  }
+  std::lock_guard<std::mutex> lk(g_cfg_mu);
+  g_host_devices = v;
+  return 0;
+}
+
+void hexl_b200_set_debug(int on) { g_debug.store(on ? 1 : 0); }
+
+int hexl_b200_sync(void* stream) {
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+void* hexl_b200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void hexl_b200_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+uint64_t hexl_b200_launch_count(void) { return launches_so_far(); }
+
+// ---- number theory
+uint64_t hexl_b200_multiply_mod(uint64_t x, uint64_t y, uint64_t q) { return nt::mul_mod(x, y, q); }
+uint64_t hexl_b200_add_uint_mod(uint64_t x, uint64_t y, uint64_t q) { return nt::add_mod(x, y, q); }
+uint64_t hexl_b200_sub_uint_mod(uint64_t x, uint64_t y, uint64_t q) { return nt::sub_mod(x, y, q); }
+uint64_t hexl_b200_pow_mod(uint64_t b, uint64_t e, uint64_t q) { return nt::pow_mod(b, e, q); }
+uint64_t hexl_b200_inverse_mod(uint64_t x, uint64_t q) { return nt::inverse_mod(x, q); }
+uint64_t hexl_b200_reverse_bits(uint64_t x, uint64_t w) { return nt::reverse_bits(x, w); }
+int hexl_b200_is_prime(uint64_t n) { return nt::is_prime(n) ? 1 : 0; }
+int hexl_b200_is_primitive_root(uint64_t r, uint64_t d, uint64_t q) { return nt::is_primitive_root(r, d, q) ? 1 : 0; }
+uint64_t hexl_b200_generate_primitive_root(uint64_t d, uint64_t q) { return nt::generate_primitive_root(d, q); }
+uint64_t hexl_b200_minimal_primitive_root(uint64_t d, uint64_t q) { return nt::minimal_primitive_root(d, q); }
+uint64_t hexl_b200_multiply_factor(uint64_t operand, uint64_t bit_shift, uint64_t q) {
+  return nt::multiply_factor(operand, bit_shift, q);
+}
+int hexl_b200_generate_primes(uint64_t* out, size_t num, size_t bit_size, int prefer_small, size_t ntt_size) {
+  std::vector<uint64_t> p = nt::generate_primes(num, bit_size, prefer_small != 0, ntt_size);
+  for (size_t i = 0; i < p.size(); ++i) out[i] = p[i];
+  return (int)p.size();
+}
+
+// ---- NTT object
+int hexl_b200_ntt_create(hexl_b200_ntt** out, uint64_t degree, uint64_t q) {
+  return create_common(out, degree, q, 0, false);
+}
+int hexl_b200_ntt_create_with_root(hexl_b200_ntt** out, uint64_t degree, uint64_t q, uint64_t root) {
+  return create_common(out, degree, q, root, true);
+}
+void hexl_b200_ntt_retain(hexl_b200_ntt* h) {
+  if (h) h->refs.fetch_add(1);
+}
+void hexl_b200_ntt_release(hexl_b200_ntt* h) {
+  if (!h || h->refs.fetch_sub(1) != 1) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (auto& kv : h->dev) {
+    if (cudaSetDevice(kv.first) == cudaSuccess) {
+      cudaFree(kv.second.fwd);
+      cudaFree(kv.second.inv);
+    }
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  cudaGetLastError();
+  delete h;
+}
+int hexl_b200_ntt_check_arguments(uint64_t degree, uint64_t q) {
+  const char* why = "";
+  return check_ntt_arguments(degree, q, &why) ? 1 : 0;
+}
+uint64_t hexl_b200_ntt_degree(const hexl_b200_ntt* h) { return h ? h->n : 0; }
+uint64_t hexl_b200_ntt_modulus(const hexl_b200_ntt* h) { return h ? h->q : 0; }
+uint64_t hexl_b200_ntt_minimal_root(const hexl_b200_ntt* h) { return h ? h->root : 0; }
+const uint64_t* hexl_b200_ntt_table(const hexl_b200_ntt* h, int which) {
+  if (!h) return nullptr;
+  switch (which) {
+    case 0: return h->w.data();
+    case 1: return h->w_precon.data();
+    case 2: return h->inv_seq.data();
+    case 3: return h->inv_seq_precon.data();
+  }
+  return nullptr;
+}
+
+int hexl_b200_ntt_forward(hexl_b200_ntt* h, uint64_t* result, const uint64_t* operand, uint64_t in_mf,
+                          uint64_t out_mf, uint64_t batch, void* stream) {
+  return ntt_compute(true, h, result, operand, in_mf, out_mf, batch, stream);
+}
+int hexl_b200_ntt_inverse(hexl_b200_ntt* h, uint64_t* result, const uint64_t* operand, uint64_t in_mf,
+                          uint64_t out_mf, uint64_t batch, void* stream) {
+  return ntt_compute(false, h, result, operand, in_mf, out_mf, batch, stream);
+}
+
+// ---- eltwise.  Checks mirror the HEXL_CHECKs at the top of each reference op.
+int hexl_b200_eltwise_add_mod(uint64_t* result, const uint64_t* op1, const uint64_t* op2, uint64_t n,
+                              uint64_t q, void* stream) {
+  // eltwise-add-mod.cpp:73-81
+  REQUIRE(result && op1 && op2, "Require result, operand1, operand2 != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(q > 1, "Require modulus > 1");
+  REQUIRE(q < (1ull << 63), "Require modulus < 2**63");
+  if (int rc = debug_bounds(op1, n, q, "operand1", {result, op1, op2})) return rc;
+  if (int rc = debug_bounds(op2, n, q, "operand2", {result, op1, op2})) return rc;
+  EltParams p{};
+  p.result = result; p.a = op1; p.b = op2; p.n = n; p.q = q;
+  return eltwise_dispatch(EltOp::AddVV, p, stream);
+}
+
+int hexl_b200_eltwise_add_mod_scalar(uint64_t* result, const uint64_t* op1, uint64_t op2, uint64_t n,
+                                     uint64_t q, void* stream) {
+  // eltwise-add-mod.cpp:95-103
+  REQUIRE(result && op1, "Require result, operand1 != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(q > 1, "Require modulus > 1");
+  REQUIRE(q < (1ull << 63), "Require modulus < 2**63");
+  REQUIRE(op2 < q, "Require operand2 < modulus");
+  if (int rc = debug_bounds(op1, n, q, "operand1", {result, op1})) return rc;
+  EltParams p{};
+  p.result = result; p.a = op1; p.n = n; p.q = q; p.scalar = op2;
+  return eltwise_dispatch(EltOp::AddVS, p, stream);
+}
+
+int hexl_b200_eltwise_sub_mod(uint64_t* result, const uint64_t* op1, const uint64_t* op2, uint64_t n,
+                              uint64_t q, void* stream) {
+  // eltwise-sub-mod.cpp:69-77
+  REQUIRE(result && op1 && op2, "Require result, operand1, operand2 != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(q > 1, "Require modulus > 1");
+  REQUIRE(q < (1ull << 63), "Require modulus < 2**63");
+  if (int rc = debug_bounds(op1, n, q, "operand1", {result, op1, op2})) return rc;
+  if (int rc = debug_bounds(op2, n, q, "operand2", {result, op1, op2})) return rc;
+  EltParams p{};
+  p.result = result; p.a = op1; p.b = op2; p.n = n; p.q = q;
+  return eltwise_dispatch(EltOp::SubVV, p, stream);
+}
+
+int hexl_b200_eltwise_sub_mod_scalar(uint64_t* result, const uint64_t* op1, uint64_t op2, uint64_t n,
+                                     uint64_t q, void* stream) {
+  // eltwise-sub-mod.cpp:91-99
+  REQUIRE(result && op1, "Require result, operand1 != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(q > 1, "Require modulus > 1");
+  REQUIRE(q < (1ull << 63), "Require modulus < 2**63");
+  REQUIRE(op2 < q, "Require operand2 < modulus");
+  if (int rc = debug_bounds(op1, n, q, "operand1", {result, op1})) return rc;
+  EltParams p{};
+  p.result = result; p.a = op1; p.n = n; p.q = q; p.scalar = op2;
+  return eltwise_dispatch(EltOp::SubVS, p, stream);
+}
+
+int hexl_b200_eltwise_mult_mod(uint64_t* result, const uint64_t* op1, const uint64_t* op2, uint64_t n,
+                               uint64_t q, uint64_t in_mf, void* stream) {
+  // eltwise-mult-mod.cpp:21-36
+  REQUIRE(result && op1 && op2, "Require result, operand1, operand2 != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(q > 1, "Require modulus > 1");
+  REQUIRE(in_mf == 1 || in_mf == 2 || in_mf == 4, "input_mod_factor must be 1, 2 or 4; got %llu", (unsigned long long)in_mf);
+  REQUIRE(q < (1ull << 62), "Require modulus < (1ULL << 62)");
+  REQUIRE(in_mf * q < (1ull << 63), "Require input_mod_factor * modulus < (1ULL << 63)");
+  if (int rc = debug_bounds(op1, n, in_mf * q, "operand1", {result, op1, op2})) return rc;
+  if (int rc = debug_bounds(op2, n, in_mf * q, "operand2", {result, op1, op2})) return rc;
+  EltParams p{};
+  p.result = result; p.a = op1; p.b = op2; p.n = n; p.q = q; p.in_mf = (int)in_mf;
+  // generalised Barrett constants, eltwise-mult-mod-internal.hpp:52-69
+  const int L = floor_log2(q) + 1;
+  p.shift = L - 2;
+  p.mu = nt::multiply_factor(1ull << (L - 2), 64, q);
+  return eltwise_dispatch(EltOp::MultVV, p, stream);
+}
+
+int hexl_b200_eltwise_fma_mod(uint64_t* result, const uint64_t* arg1, uint64_t arg2, const uint64_t* arg3,
+                              uint64_t n, uint64_t q, uint64_t in_mf, void* stream) {
+  // eltwise-fma-mod.cpp:20-40
+  REQUIRE(result && arg1, "Require result, arg1 != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(q > 1, "Require modulus > 1");
+  REQUIRE(q < (1ull << 61), "Require modulus < (1ULL << 61)");
+  REQUIRE(in_mf == 1 || in_mf == 2 || in_mf == 4 || in_mf == 8,
+          "input_mod_factor must be 1, 2, 4, or 8. Got %llu", (unsigned long long)in_mf);
+  REQUIRE(arg2 < in_mf * q, "arg2 exceeds bound input_mod_factor * modulus");
+  if (int rc = debug_bounds(arg1, n, in_mf * q, "arg1", {result, arg1, arg3})) return rc;
+  if (int rc = debug_bounds(arg3, n, in_mf * q, "arg3", {result, arg1, arg3})) return rc;
+  EltParams p{};
+  p.result = result; p.a = arg1; p.b = arg3; p.n = n; p.q = q; p.in_mf = (int)in_mf;
+  uint64_t s = arg2;  // ReduceMod<in_mf>(arg2), eltwise-fma-mod-internal.hpp:16-17
+  if (in_mf >= 8 && s >= 4 * q) s -= 4 * q;
+  if (in_mf >= 4 && s >= 2 * q) s -= 2 * q;
+  if (in_mf >= 2 && s >= q) s -= q;
+  p.scalar = s;
+  p.scalar_p = nt::multiply_factor(s, 64, q);
+  return eltwise_dispatch(arg3 ? EltOp::Fma : EltOp::FmaNoAdd, p, stream);
+}
+
+int hexl_b200_eltwise_reduce_mod(uint64_t* result, const uint64_t* operand, uint64_t n, uint64_t q,
+                                 uint64_t in_mf, uint64_t out_mf, void* stream) {
+  // eltwise-reduce-mod.cpp:84-92
+  REQUIRE(result && operand, "Require result, operand != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(q > 1, "Require modulus > 1");
+  REQUIRE(in_mf == q || in_mf == 2 || in_mf == 4, "input_mod_factor must be modulus or 2 or 4; got %llu",
+          (unsigned long long)in_mf);
+  REQUIRE(out_mf == 1 || out_mf == 2, "output_mod_factor must be 1 or 2; got %llu", (unsigned long long)out_mf);
+  EltParams p{};
+  p.result = result; p.a = operand; p.n = n; p.q = q; p.out_mf = (int)out_mf;
+  if (in_mf == out_mf) {  // eltwise-reduce-mod.cpp:94-99: plain copy (no-op in place)
+    if (result == operand) return 0;
+    return eltwise_dispatch(EltOp::Copy, p, stream);
+  }
+  p.in_mf = (in_mf == q) ? 0 : (int)in_mf;
+  p.mu = nt::multiply_factor(1, 64, q);
+  return eltwise_dispatch(EltOp::Reduce, p, stream);
+}
+
+int hexl_b200_eltwise_cmp_add(uint64_t* result, const uint64_t* op1, uint64_t n, int cmp, uint64_t bound,
+                              uint64_t diff, void* stream) {
+  // eltwise-cmp-add.cpp:18-21
+  REQUIRE(result && op1, "Require result, operand1 != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(diff != 0, "Require diff != 0");
+  REQUIRE(cmp >= 0 && cmp <= 7, "cmp must be a CMPINT value (0..7)");
+  EltParams p{};
+  p.result = result; p.a = op1; p.n = n; p.scalar = bound; p.scalar_p = diff; p.cmp = cmp;
+  return eltwise_dispatch(EltOp::CmpAdd, p, stream);
+}
+
+int hexl_b200_eltwise_cmp_sub_mod(uint64_t* result, const uint64_t* op1, uint64_t n, uint64_t q, int cmp,
+                                  uint64_t bound, uint64_t diff, void* stream) {
+  // eltwise-cmp-sub-mod.cpp:21-25,50-55
+  REQUIRE(result && op1, "Require result, operand1 != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(q > 1, "Require modulus > 1");
+  REQUIRE(diff != 0, "Require diff != 0");
+  REQUIRE(diff < q, "Diff >= modulus");
+  REQUIRE(cmp >= 0 && cmp <= 7, "cmp must be a CMPINT value (0..7)");
+  EltParams p{};
+  p.result = result; p.a = op1; p.n = n; p.q = q; p.scalar = bound; p.scalar_p = diff; p.cmp = cmp;
+  p.mu = nt::multiply_factor(1, 64, q);
+  return eltwise_dispatch(EltOp::CmpSubMod, p, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+/* hexl_b200.h -- C ABI of libhexl_b200.so, the Blackwell (sm_100a) drop-in for the
+ * intel/hexl hot path: NTT::ComputeForward / ComputeInverse and the seven
+ * Eltwise*Mod operations.
+ *
+ * Every entry point names the reference interface it replaces (file:line relative
+ * to the intel/hexl v1.2.5 tree).  The C++ headers under include/hexl/ re-create
+ * the reference's `intel::hexl` API (same names, overloads, defaults) as inline
+ * forwarders to these symbols, so SEAL/OpenFHE-style callers re-link unchanged;
+ * INTEGRATION.md shows the binding a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; no C++ or torch types.
+ *  - Every data pointer may be a DEVICE pointer (cudaMalloc / torch tensor
+ *    storage; the call is enqueued on `stream` and returns without synchronising)
+ *    or a HOST pointer (pageable or pinned; the call stages the buffers through
+ *    the GPU -- H2D, kernel, D2H, chunked so copies and kernels overlap -- and
+ *    returns when `result` is complete).  All data pointers of one call must be
+ *    of the same kind.  `result` may alias an input (in place), as in the
+ *    reference (test/test-ntt.cpp:240-243).
+ *  - `stream` is a cudaStream_t passed as void*; NULL = the legacy default stream.
+ *  - Batched calls take `batch` independent units laid out back to back
+ *    (unit u at offset u*n elements); batch = 1 is the reference's one-call shape.
+ *  - Return value: 0 on success, negative hexl_b200_status otherwise;
+ *    hexl_b200_last_error() returns a thread-local message.  There is NO CPU
+ *    fallback: without a usable CUDA device every compute entry point fails
+ *    with HEXL_B200_ERR_NO_DEVICE.
+ *  - Argument validation mirrors the reference's HEXL_CHECKs
+ *    (e.g. hexl/ntt/ntt-internal.cpp:191-200, hexl/eltwise/eltwise-fma-mod.cpp:20-40).
+ *    Cheap checks (null, n == 0, mod factors, modulus range) are always on;
+ *    the O(n) input-range checks only when hexl_b200_set_debug(1) was called
+ *    (the reference does them only in HEXL_DEBUG builds, check.hpp:12-44).
+ */
+#ifndef HEXL_B200_H
+#define HEXL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum hexl_b200_status {
+  HEXL_B200_OK = 0,
+  HEXL_B200_ERR_INVALID_ARG = -1, /* a HEXL_CHECK of the reference would fire */
+  HEXL_B200_ERR_NO_DEVICE = -2,   /* no CUDA device / driver */
+  HEXL_B200_ERR_CUDA = -3,        /* a CUDA runtime call failed */
+  HEXL_B200_ERR_ALLOC = -4,
+  HEXL_B200_ERR_MIXED_POINTERS = -5 /* host and device pointers in one call */
+} hexl_b200_status;
+
+typedef struct hexl_b200_ntt hexl_b200_ntt; /* opaque, reference-counted */
+
+/* ---- library / device management (no counterpart in the reference: it is CPU-only) */
+const char* hexl_b200_version(void);
+const char* hexl_b200_last_error(void);
+int hexl_b200_device_count(void);
+/* Devices used for HOST-pointer calls with batch > 1: units are split into
+ * contiguous blocks, one block per listed device (no inter-GPU traffic).
+ * Default: the calling thread's current device only. */
+int hexl_b200_set_host_devices(const int* devices, int count);
+void hexl_b200_set_debug(int on); /* O(n) input-range checks, like HEXL_DEBUG */
+int hexl_b200_sync(void* stream);
+/* Pinned host memory so host-pointer calls DMA at full PCIe rate (the
+ * reference's AllocatorBase hook, hexl/include/hexl/util/allocator.hpp:12-24,
+ * is the place a caller would plug these in). */
+void* hexl_b200_host_alloc(size_t bytes);
+void hexl_b200_host_free(void* p);
+/* number of kernel launches this library has issued in this process */
+uint64_t hexl_b200_launch_count(void);
+
+/* ---- number theory (host side; hexl/include/hexl/number-theory/number-theory.hpp) */
+uint64_t hexl_b200_multiply_mod(uint64_t x, uint64_t y, uint64_t q);      /* :83  */
+uint64_t hexl_b200_add_uint_mod(uint64_t x, uint64_t y, uint64_t q);      /* :95  */
+uint64_t hexl_b200_sub_uint_mod(uint64_t x, uint64_t y, uint64_t q);      /* :99  */
+uint64_t hexl_b200_pow_mod(uint64_t base, uint64_t exp, uint64_t q);      /* :102 */
+uint64_t hexl_b200_inverse_mod(uint64_t x, uint64_t q);                   /* :79  */
+uint64_t hexl_b200_reverse_bits(uint64_t x, uint64_t bit_width);          /* :75  */
+int hexl_b200_is_prime(uint64_t n);                                       /* :166 */
+int hexl_b200_is_primitive_root(uint64_t root, uint64_t degree, uint64_t q); /* :108 */
+uint64_t hexl_b200_generate_primitive_root(uint64_t degree, uint64_t q);  /* :112 */
+uint64_t hexl_b200_minimal_primitive_root(uint64_t degree, uint64_t q);   /* :117 */
+/* floor(operand * 2^bit_shift / q), bit_shift in {32, 52, 64} (MultiplyFactor, :19-51) */
+uint64_t hexl_b200_multiply_factor(uint64_t operand, uint64_t bit_shift, uint64_t q);
+/* GeneratePrimes (:181): writes up to num primes, returns how many were found */
+int hexl_b200_generate_primes(uint64_t* out, size_t num, size_t bit_size, int prefer_small,
+                              size_t ntt_size);
+
+/* ---- NTT object (class NTT, hexl/include/hexl/ntt/ntt.hpp:22-293) ---------------- */
+/* NTT(degree, q): ntt.hpp:54 -- uses the minimal primitive 2N-th root */
+int hexl_b200_ntt_create(hexl_b200_ntt** out, uint64_t degree, uint64_t q);
+/* NTT(degree, q, root_of_unity): ntt.hpp:75 */
+int hexl_b200_ntt_create_with_root(hexl_b200_ntt** out, uint64_t degree, uint64_t q,
+                                   uint64_t root_of_unity);
+void hexl_b200_ntt_retain(hexl_b200_ntt* h);  /* NTT is copyable in the reference */
+void hexl_b200_ntt_release(hexl_b200_ntt* h); /* ~NTT */
+/* NTT::CheckArguments (ntt.hpp:90, ntt-internal.cpp:171-186): 1 if valid */
+int hexl_b200_ntt_check_arguments(uint64_t degree, uint64_t q);
+uint64_t hexl_b200_ntt_degree(const hexl_b200_ntt* h);           /* GetDegree  :119 */
+uint64_t hexl_b200_ntt_modulus(const hexl_b200_ntt* h);          /* GetModulus :122 */
+uint64_t hexl_b200_ntt_minimal_root(const hexl_b200_ntt* h);     /* GetMinimalRootOfUnity :116 */
+/* Host copies of the tables in the reference's layouts (getters ntt.hpp:125-194).
+ * `which`: 0 root powers (bit-reversed slots), 1 their 64-bit Shoup factors,
+ * 2 inverse root powers (stage-sequential order of ntt-internal.cpp:144-154),
+ * 3 their 64-bit Shoup factors.  Returns a pointer valid for the handle's life. */
+const uint64_t* hexl_b200_ntt_table(const hexl_b200_ntt* h, int which);
+
+/* NTT::ComputeForward (ntt.hpp:99; ntt-internal.cpp:188-250): natural-order input,
+ * bit-reversed output.  in_mf in {1,2,4}: inputs < in_mf*q; out_mf in {1,4}:
+ * outputs in [0, out_mf*q).  `batch` polynomials back to back. */
+int hexl_b200_ntt_forward(hexl_b200_ntt* h, uint64_t* result, const uint64_t* operand,
+                          uint64_t input_mod_factor, uint64_t output_mod_factor,
+                          uint64_t batch, void* stream);
+/* NTT::ComputeInverse (ntt.hpp:109; ntt-internal.cpp:252-310): bit-reversed input,
+ * natural-order output, includes the 1/N scale.  in_mf in {1,2}, out_mf in {1,2}. */
+int hexl_b200_ntt_inverse(hexl_b200_ntt* h, uint64_t* result, const uint64_t* operand,
+                          uint64_t input_mod_factor, uint64_t output_mod_factor,
+                          uint64_t batch, void* stream);
+
+/* ---- element-wise operations (hexl/include/hexl/eltwise/ *.hpp) -------------------
+ * n = number of elements (for batched use pass n = batch * N: the ops are
+ * position-independent). */
+/* EltwiseAddMod vector-vector, eltwise-add-mod.hpp:22 */
+int hexl_b200_eltwise_add_mod(uint64_t* result, const uint64_t* operand1,
+                              const uint64_t* operand2, uint64_t n, uint64_t modulus,
+                              void* stream);
+/* EltwiseAddMod vector-scalar, eltwise-add-mod.hpp:36 */
+int hexl_b200_eltwise_add_mod_scalar(uint64_t* result, const uint64_t* operand1,
+                                     uint64_t operand2, uint64_t n, uint64_t modulus,
+                                     void* stream);
+/* EltwiseSubMod vector-vector, eltwise-sub-mod.hpp:22 */
+int hexl_b200_eltwise_sub_mod(uint64_t* result, const uint64_t* operand1,
+                              const uint64_t* operand2, uint64_t n, uint64_t modulus,
+                              void* stream);
+/* EltwiseSubMod vector-scalar, eltwise-sub-mod.hpp:36 */
+int hexl_b200_eltwise_sub_mod_scalar(uint64_t* result, const uint64_t* operand1,
+                                     uint64_t operand2, uint64_t n, uint64_t modulus,
+                                     void* stream);
+/* EltwiseMultMod, eltwise-mult-mod.hpp:23; in_mf in {1,2,4} */
+int hexl_b200_eltwise_mult_mod(uint64_t* result, const uint64_t* operand1,
+                               const uint64_t* operand2, uint64_t n, uint64_t modulus,
+                               uint64_t input_mod_factor, void* stream);
+/* EltwiseFMAMod, eltwise-fma-mod.hpp:22; arg3 may be NULL; in_mf in {1,2,4,8} */
+int hexl_b200_eltwise_fma_mod(uint64_t* result, const uint64_t* arg1, uint64_t arg2,
+                              const uint64_t* arg3, uint64_t n, uint64_t modulus,
+                              uint64_t input_mod_factor, void* stream);
+/* EltwiseReduceMod, eltwise-reduce-mod.hpp:24; in_mf in {modulus,2,4}, out_mf in {1,2} */
+int hexl_b200_eltwise_reduce_mod(uint64_t* result, const uint64_t* operand, uint64_t n,
+                                 uint64_t modulus, uint64_t input_mod_factor,
+                                 uint64_t output_mod_factor, void* stream);
+/* EltwiseCmpAdd, eltwise-cmp-add.hpp:22; cmp = CMPINT value 0..7 (util.hpp:16-25) */
+int hexl_b200_eltwise_cmp_add(uint64_t* result, const uint64_t* operand1, uint64_t n,
+                              int cmp, uint64_t bound, uint64_t diff, void* stream);
+/* EltwiseCmpSubMod, eltwise-cmp-sub-mod.hpp:24 */
+int hexl_b200_eltwise_cmp_sub_mod(uint64_t* result, const uint64_t* operand1, uint64_t n,
+                                  uint64_t modulus, int cmp, uint64_t bound, uint64_t diff,
+                                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEXL_B200_H */

@@ -1,0 +1,491 @@
+/* ==========================================================================
+ * TEST INFRASTRUCTURE ONLY -- NOT PRODUCT CODE.
+ *
+ * Plain-C restatement of the reference's (intel/hexl v1.2.5, /root/reference)
+ * scalar "native C++" algorithms for the one hot path this repo rebuilds:
+ * NTT::ComputeForward / ComputeInverse and the seven Eltwise*Mod operations,
+ * plus the number-theory helpers their table construction needs.  Each
+ * function cites the reference file:line it follows.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may build, load or call this file; nothing under hexl_b200/ may.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function
+ * here against the reference's own known-answer vectors (the JSON files under tests/golden/,
+ * restated from test/test-ntt.cpp, test/test-number-theory.cpp,
+ * test/test-eltwise-*.cpp, example/example.cpp) and tests/test_oracle_vs_ref.py
+ * checks it against the compiled reference itself (oracle/_ref) on random
+ * inputs, including bit-for-bit equality of the lazy (out_mf 4 / 2) outputs
+ * with the reference's scalar tier.
+ * ========================================================================== */
+#include "hexl_oracle.h"
+
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef unsigned __int128 u128;
+
+/* hi 64 bits of a 64x64 product: hexl/include/hexl/util/gcc.hpp:49-54 (BitShift 64) */
+static inline uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((u128)a * b) >> 64); }
+
+/* ---------------------------------------------------------------- number theory */
+
+/* hexl/number-theory/number-theory.cpp:44-52 with gcc.hpp:20-28 (a true 128-bit %) */
+uint64_t orc_multiply_mod(uint64_t x, uint64_t y, uint64_t q) {
+  return (uint64_t)(((u128)x * y) % q);
+}
+
+/* number-theory.cpp:61-66 */
+uint64_t orc_add_mod(uint64_t x, uint64_t y, uint64_t q) {
+  uint64_t s = x + y;
+  return s >= q ? s - q : s;
+}
+
+/* number-theory.cpp:68-73 */
+uint64_t orc_sub_mod(uint64_t x, uint64_t y, uint64_t q) {
+  uint64_t d = (x + q) - y;
+  return d >= q ? d - q : d;
+}
+
+/* number-theory.cpp:76-87: right-to-left square and multiply */
+uint64_t orc_pow_mod(uint64_t base, uint64_t exp, uint64_t q) {
+  uint64_t acc = 1;
+  base %= q;
+  for (; exp; exp >>= 1) {
+    if (exp & 1) acc = orc_multiply_mod(acc, base, q);
+    base = orc_multiply_mod(base, base, q);
+  }
+  return acc;
+}
+
+/* number-theory.cpp:13-42: extended Euclid, result made non-negative */
+uint64_t orc_inverse_mod(uint64_t x, uint64_t q) {
+  if (q == 1) return 0;
+  int64_t m0 = (int64_t)q, s_prev = 1, s_cur = 0; /* x*s_prev == a (mod q) invariant */
+  uint64_t a = x % q, b = q;
+  while (a > 1) {
+    int64_t quot = (int64_t)(a / b);
+    uint64_t rem = a % b;
+    a = b;
+    b = rem;
+    int64_t s_next = s_prev - quot * s_cur;
+    s_prev = s_cur;
+    s_cur = s_next;
+  }
+  if (s_prev < 0) s_prev += m0;
+  return (uint64_t)s_prev;
+}
+
+/* number-theory.cpp:150-163 */
+uint64_t orc_reverse_bits(uint64_t x, uint64_t bit_width) {
+  uint64_t r = 0;
+  for (uint64_t i = 0; i < bit_width; ++i) r |= ((x >> i) & 1ULL) << (bit_width - 1 - i);
+  return r;
+}
+
+/* number-theory.cpp:166-212: deterministic Miller-Rabin, 12 fixed bases */
+int orc_is_prime(uint64_t n) {
+  static const uint64_t bases[12] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37};
+  for (int i = 0; i < 12; ++i) {
+    if (n == bases[i]) return 1;
+    if (n % bases[i] == 0) return 0;
+  }
+  if (n < 2) return 0;
+  uint64_t d = n - 1;
+  unsigned r = 0;
+  while ((d & 1) == 0) {
+    d >>= 1;
+    ++r;
+  }
+  for (int i = 0; i < 12; ++i) {
+    uint64_t x = orc_pow_mod(bases[i], d, n);
+    if (x == 1 || x == n - 1) continue;
+    int witness_composite = 1;
+    for (unsigned k = 1; k < r; ++k) {
+      x = orc_multiply_mod(x, x, n);
+      if (x == n - 1) {
+        witness_composite = 0;
+        break;
+      }
+    }
+    if (witness_composite) return 0;
+  }
+  return 1;
+}
+
+/* number-theory.cpp:91-102: root^(degree/2) == -1 */
+int orc_is_primitive_root(uint64_t root, uint64_t degree, uint64_t q) {
+  if (root == 0) return 0;
+  return orc_pow_mod(root, degree / 2, q) == q - 1;
+}
+
+/* number-theory.cpp:128-148.  The reference starts from a randomly generated
+ * primitive root (:106-124) and takes the minimum over its odd powers; the odd
+ * powers of ANY primitive degree-th root enumerate ALL primitive degree-th
+ * roots, so the result does not depend on the starting root.  Here the start is
+ * found deterministically (g = 2, 3, ... raised to (q-1)/degree). */
+uint64_t orc_minimal_primitive_root(uint64_t degree, uint64_t q) {
+  uint64_t cofactor = (q - 1) / degree, start = 0;
+  for (uint64_t g = 2; g < q && !start; ++g) {
+    uint64_t cand = orc_pow_mod(g, cofactor, q);
+    if (orc_is_primitive_root(cand, degree, q)) start = cand;
+  }
+  if (!start) return 0;
+  uint64_t step = orc_multiply_mod(start, start, q), cur = start, best = start;
+  for (uint64_t i = 0; i < degree / 2; ++i) {
+    if (cur < best) best = cur;
+    cur = orc_multiply_mod(cur, step, q);
+  }
+  return best;
+}
+
+/* number-theory.cpp:214-261: primes == 1 (mod 2*ntt_size), ascending from
+ * 2^bits + 1 (prefer_small) or descending from below 2^(bits+1). */
+int orc_generate_primes(uint64_t* out, uint64_t num, uint64_t bits, int prefer_small,
+                        uint64_t ntt_size) {
+  int64_t lo = ((int64_t)1 << bits) + 1, hi = ((int64_t)1 << (bits + 1)) - 1;
+  int64_t stride = 2 * (int64_t)ntt_size;
+  int64_t cand = prefer_small ? lo : hi - (hi % stride) + 1;
+  uint64_t found = 0;
+  while (prefer_small ? cand < hi : cand > lo) {
+    if (orc_is_prime((uint64_t)cand)) {
+      out[found++] = (uint64_t)cand;
+      if (found == num) break;
+    }
+    cand += prefer_small ? stride : -stride;
+  }
+  return (int)found;
+}
+
+/* hexl/include/hexl/number-theory/number-theory.hpp:29-40:
+ * floor(operand * 2^bit_shift / q), low 64 bits */
+uint64_t orc_multiply_factor(uint64_t operand, unsigned bit_shift, uint64_t q) {
+  return (uint64_t)((((u128)operand) << bit_shift) / q);
+}
+
+/* ---------------------------------------------------------------------- tables */
+
+/* hexl/ntt/ntt-internal.cpp:54-72 (powers in bit-reversed slots), :113-139
+ * (64-bit Shoup factors) and :144-168 (inverse powers re-ordered so that the
+ * inverse transform consumes them sequentially: groups of the m = n/2 stage
+ * first, then m = n/4, ..., m = 1). */
+void orc_ntt_tables(uint64_t n, uint64_t q, uint64_t root, uint64_t* w, uint64_t* w_precon,
+                    uint64_t* inv_w, uint64_t* inv_w_precon) {
+  unsigned logn = 0;
+  while ((1ULL << logn) < n) ++logn;
+  uint64_t* fwd = (uint64_t*)malloc(n * sizeof(uint64_t));
+  uint64_t* inv_br = (uint64_t*)malloc(n * sizeof(uint64_t));
+  uint64_t power = 1;
+  fwd[0] = 1;
+  inv_br[0] = 1;
+  for (uint64_t i = 1; i < n; ++i) {
+    power = orc_multiply_mod(power, root, q); /* root^i */
+    uint64_t slot = orc_reverse_bits(i, logn);
+    fwd[slot] = power;
+    inv_br[slot] = orc_inverse_mod(power, q);
+  }
+  uint64_t pos = 1;
+  uint64_t* inv_seq = (uint64_t*)malloc(n * sizeof(uint64_t));
+  inv_seq[0] = inv_br[0];
+  for (uint64_t m = n >> 1; m > 0; m >>= 1)
+    for (uint64_t i = 0; i < m; ++i) inv_seq[pos++] = inv_br[m + i];
+  for (uint64_t i = 0; i < n; ++i) {
+    if (w) w[i] = fwd[i];
+    if (w_precon) w_precon[i] = orc_multiply_factor(fwd[i], 64, q);
+    if (inv_w) inv_w[i] = inv_seq[i];
+    if (inv_w_precon) inv_w_precon[i] = orc_multiply_factor(inv_seq[i], 64, q);
+  }
+  free(fwd);
+  free(inv_br);
+  free(inv_seq);
+}
+
+/* ------------------------------------------------------------------ transforms */
+
+/* number-theory.hpp:127-141: x*y - floor(x*y'/2^64)*q, in [0, 2q) */
+static inline uint64_t shoup_lazy(uint64_t x, uint64_t y, uint64_t y_precon, uint64_t q) {
+  return y * x - mulhi64(x, y_precon) * q;
+}
+
+/* hexl/ntt/ntt-radix-2.cpp:17-261 with the butterfly of ntt-default.hpp:28-42.
+ * Values stay in [0, 4q); the first stage reads `operand`, later stages work in
+ * place on `result`; the final sweep (:254-260) is ReduceMod<4> when out_mf == 1. */
+static void fwd_one(uint64_t* result, const uint64_t* operand, uint64_t n, uint64_t q,
+                    const uint64_t* w, const uint64_t* wp, uint64_t out_mf) {
+  const uint64_t two_q = q << 1;
+  const uint64_t* src = operand;
+  uint64_t t = n >> 1;
+  for (uint64_t m = 1; m < n; m <<= 1, t >>= 1) {
+    for (uint64_t i = 0; i < m; ++i) {
+      const uint64_t W = w[m + i], Wp = wp[m + i];
+      const uint64_t base = 2 * i * t;
+      for (uint64_t j = base; j < base + t; ++j) {
+        uint64_t X = src[j], Y = src[j + t];
+        uint64_t tx = X >= two_q ? X - two_q : X;
+        uint64_t T = shoup_lazy(Y, W, Wp, q);
+        result[j] = tx + T;
+        result[j + t] = tx + two_q - T;
+      }
+    }
+    src = result;
+  }
+  if (out_mf == 1) {
+    for (uint64_t i = 0; i < n; ++i) {
+      uint64_t v = result[i];
+      if (v >= two_q) v -= two_q;
+      if (v >= q) v -= q;
+      result[i] = v;
+    }
+  }
+}
+
+/* ntt-radix-2.cpp:330-519 with the butterfly of ntt-default.hpp:112-125.
+ * Values stay in [0, 2q); stages m = n/2 .. 2 consume inv_w sequentially from
+ * index 1; the last stage (:484-509) folds N^-1 into both outputs; :511-518 is
+ * ReduceMod<2> when out_mf == 1. */
+static void inv_one(uint64_t* result, const uint64_t* operand, uint64_t n, uint64_t q,
+                    const uint64_t* iw, const uint64_t* iwp, uint64_t out_mf) {
+  const uint64_t two_q = q << 1, half = n >> 1;
+  const uint64_t* src = operand;
+  uint64_t t = 1, ridx = 1;
+  for (uint64_t m = half; m > 1; m >>= 1, t <<= 1) {
+    for (uint64_t i = 0; i < m; ++i, ++ridx) {
+      const uint64_t W = iw[ridx], Wp = iwp[ridx];
+      const uint64_t base = 2 * i * t;
+      for (uint64_t j = base; j < base + t; ++j) {
+        uint64_t X = src[j], Y = src[j + t];
+        uint64_t sum = X + Y;
+        uint64_t dif = X + two_q - Y;
+        result[j] = sum >= two_q ? sum - two_q : sum;
+        result[j + t] = shoup_lazy(dif, W, Wp, q);
+      }
+    }
+    src = result;
+  }
+  if (src != result && result != operand) memcpy(result, operand, n * sizeof(uint64_t)); /* n == 2 */
+  const uint64_t W = iw[n - 1];
+  const uint64_t inv_n = orc_inverse_mod(n, q);
+  const uint64_t inv_n_p = orc_multiply_factor(inv_n, 64, q);
+  const uint64_t inv_n_w = orc_multiply_mod(inv_n, W, q);
+  const uint64_t inv_n_w_p = orc_multiply_factor(inv_n_w, 64, q);
+  for (uint64_t j = 0; j < half; ++j) {
+    uint64_t X = result[j], Y = result[j + half];
+    uint64_t tx = orc_add_mod(X, Y, two_q);
+    uint64_t ty = X + two_q - Y;
+    result[j] = shoup_lazy(tx, inv_n, inv_n_p, q);
+    result[j + half] = shoup_lazy(ty, inv_n_w, inv_n_w_p, q);
+  }
+  if (out_mf == 1)
+    for (uint64_t i = 0; i < n; ++i)
+      if (result[i] >= q) result[i] -= q;
+}
+
+typedef struct {
+  uint64_t *result;
+  const uint64_t *operand, *t0, *t1;
+  uint64_t n, q, out_mf, lo, hi;
+  int forward;
+} ntt_job;
+
+static void* ntt_worker(void* arg) {
+  ntt_job* j = (ntt_job*)arg;
+  for (uint64_t u = j->lo; u < j->hi; ++u) {
+    if (j->forward)
+      fwd_one(j->result + u * j->n, j->operand + u * j->n, j->n, j->q, j->t0, j->t1, j->out_mf);
+    else
+      inv_one(j->result + u * j->n, j->operand + u * j->n, j->n, j->q, j->t0, j->t1, j->out_mf);
+  }
+  return NULL;
+}
+
+static void ntt_batch(int forward, uint64_t* result, const uint64_t* operand, uint64_t n,
+                      uint64_t q, const uint64_t* t0, const uint64_t* t1, uint64_t out_mf,
+                      uint64_t batch, int threads) {
+  if (threads < 1) threads = 1;
+  if ((uint64_t)threads > batch) threads = (int)batch;
+  ntt_job* jobs = (ntt_job*)malloc(sizeof(ntt_job) * (size_t)(threads > 0 ? threads : 1));
+  pthread_t* tids = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)(threads > 0 ? threads : 1));
+  for (int k = 0; k < threads; ++k) {
+    ntt_job j = {result, operand, t0,        t1,
+                 n,      q,       out_mf,    batch * (uint64_t)k / (uint64_t)threads,
+                 batch * (uint64_t)(k + 1) / (uint64_t)threads, forward};
+    jobs[k] = j;
+    if (threads == 1)
+      ntt_worker(&jobs[k]);
+    else
+      pthread_create(&tids[k], NULL, ntt_worker, &jobs[k]);
+  }
+  if (threads > 1)
+    for (int k = 0; k < threads; ++k) pthread_join(tids[k], NULL);
+  free(jobs);
+  free(tids);
+}
+
+void orc_ntt_forward(uint64_t* result, const uint64_t* operand, uint64_t n, uint64_t q,
+                     const uint64_t* w, const uint64_t* w_precon, uint64_t in_mf,
+                     uint64_t out_mf, uint64_t batch, int threads) {
+  (void)in_mf; /* inputs in [0, 4q) are all handled alike: ntt-radix-2.cpp:33 */
+  ntt_batch(1, result, operand, n, q, w, w_precon, out_mf, batch, threads);
+}
+
+void orc_ntt_inverse(uint64_t* result, const uint64_t* operand, uint64_t n, uint64_t q,
+                     const uint64_t* inv_w, const uint64_t* inv_w_precon, uint64_t in_mf,
+                     uint64_t out_mf, uint64_t batch, int threads) {
+  (void)in_mf; /* ntt-radix-2.cpp:343 */
+  ntt_batch(0, result, operand, n, q, inv_w, inv_w_precon, out_mf, batch, threads);
+}
+
+/* ntt-radix-2.cpp:263-291: textbook CT, fully reduced at every step */
+void orc_ntt_forward_textbook(uint64_t* a, uint64_t n, uint64_t q, const uint64_t* w) {
+  uint64_t t = n >> 1;
+  for (uint64_t m = 1; m < n; m <<= 1, t >>= 1)
+    for (uint64_t i = 0; i < m; ++i)
+      for (uint64_t j = 2 * i * t; j < 2 * i * t + t; ++j) {
+        uint64_t x = a[j], wy = orc_multiply_mod(a[j + t], w[m + i], q);
+        a[j] = orc_add_mod(x, wy, q);
+        a[j + t] = orc_sub_mod(x, wy, q);
+      }
+}
+
+/* ntt-radix-2.cpp:293-328: textbook GS, then a separate multiply by N^-1 */
+void orc_ntt_inverse_textbook(uint64_t* a, uint64_t n, uint64_t q, const uint64_t* inv_w) {
+  uint64_t t = 1, ridx = 1;
+  for (uint64_t m = n >> 1; m >= 1; m >>= 1, t <<= 1)
+    for (uint64_t i = 0; i < m; ++i, ++ridx)
+      for (uint64_t j = 2 * i * t; j < 2 * i * t + t; ++j) {
+        uint64_t x = a[j], y = a[j + t];
+        a[j] = orc_add_mod(x, y, q);
+        a[j + t] = orc_multiply_mod(inv_w[ridx], orc_sub_mod(x, y, q), q);
+      }
+  uint64_t inv_n = orc_inverse_mod(n, q);
+  for (uint64_t i = 0; i < n; ++i) a[i] = orc_multiply_mod(a[i], inv_n, q);
+}
+
+/* ---------------------------------------------------------------- element-wise */
+
+/* number-theory.hpp:214-258: conditional subtractions from [0, k*q) to [0, q) */
+static inline uint64_t reduce_from(uint64_t x, uint64_t q, uint64_t k) {
+  if (k >= 8 && x >= 4 * q) x -= 4 * q;
+  if (k >= 4 && x >= 2 * q) x -= 2 * q;
+  if (k >= 2 && x >= q) x -= q;
+  return x;
+}
+
+/* hexl/eltwise/eltwise-add-mod.cpp:16-42 */
+void orc_eltwise_add_mod(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t n,
+                         uint64_t q) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t s = a[i] + b[i];
+    r[i] = s >= q ? s - q : s;
+  }
+}
+
+/* eltwise-add-mod.cpp:44-69 */
+void orc_eltwise_add_mod_scalar(uint64_t* r, const uint64_t* a, uint64_t b, uint64_t n,
+                                uint64_t q) {
+  const uint64_t gap = q - b;
+  for (uint64_t i = 0; i < n; ++i) r[i] = a[i] >= gap ? a[i] - gap : a[i] + b;
+}
+
+/* hexl/eltwise/eltwise-sub-mod.cpp:16-42 */
+void orc_eltwise_sub_mod(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t n,
+                         uint64_t q) {
+  for (uint64_t i = 0; i < n; ++i) r[i] = a[i] >= b[i] ? a[i] - b[i] : a[i] + q - b[i];
+}
+
+/* eltwise-sub-mod.cpp:44-65 */
+void orc_eltwise_sub_mod_scalar(uint64_t* r, const uint64_t* a, uint64_t b, uint64_t n,
+                                uint64_t q) {
+  for (uint64_t i = 0; i < n; ++i) r[i] = a[i] >= b ? a[i] - b : a[i] + q - b;
+}
+
+/* hexl/eltwise/eltwise-mult-mod-internal.hpp:33-101: generalised Barrett with
+ * alpha = 62, beta = -2: c1 = floor(U / 2^(L-2)), q_hat = hi64(c1 * mu) with
+ * mu = floor(2^(L+62) / q), L = floor(log2 q) + 1; one conditional subtraction. */
+void orc_eltwise_mult_mod(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t n,
+                          uint64_t q, uint64_t in_mf) {
+  unsigned L = 64 - (unsigned)__builtin_clzll(q); /* Log2(q) + 1 */
+  unsigned shift = L - 2;
+  uint64_t mu = orc_multiply_factor(1ULL << (L + 62 - 64), 64, q);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t x = reduce_from(a[i], q, in_mf), y = reduce_from(b[i], q, in_mf);
+    u128 U = (u128)x * y;
+    uint64_t c1 = (uint64_t)(U >> shift);
+    uint64_t z = (uint64_t)U - mulhi64(c1, mu) * q;
+    r[i] = z >= q ? z - q : z;
+  }
+}
+
+/* hexl/eltwise/eltwise-fma-mod-internal.hpp:11-39: Shoup multiply by the
+ * (reduced) scalar with one conditional subtraction (number-theory.cpp:54-59),
+ * then a modular add of the (reduced) addend. */
+void orc_eltwise_fma_mod(uint64_t* r, const uint64_t* a, uint64_t b, const uint64_t* c,
+                         uint64_t n, uint64_t q, uint64_t in_mf) {
+  b = reduce_from(b, q, in_mf);
+  const uint64_t bp = orc_multiply_factor(b, 64, q);
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t x = reduce_from(a[i], q, in_mf);
+    uint64_t p = shoup_lazy(x, b, bp, q);
+    if (p >= q) p -= q;
+    if (c) p = orc_add_mod(p, reduce_from(c[i], q, in_mf), q);
+    r[i] = p;
+  }
+}
+
+/* hexl/eltwise/eltwise-reduce-mod.cpp:16-79 (and the equal-factor copy of
+ * :94-99).  in_mf == q means "arbitrary 64-bit input": Barrett-64 with
+ * floor(2^64/q) (number-theory.hpp:195-205), applied only when x >= q. */
+void orc_eltwise_reduce_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_t q,
+                            uint64_t in_mf, uint64_t out_mf) {
+  if (in_mf == out_mf) {
+    if (r != a) memmove(r, a, n * sizeof(uint64_t));
+    return;
+  }
+  const uint64_t mu = orc_multiply_factor(1, 64, q), two_q = q << 1;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t x = a[i];
+    if (in_mf == q) {
+      if (x >= q) {
+        x = x - mulhi64(x, mu) * q;
+        if (out_mf == 1 && x >= q) x -= q;
+      }
+    } else if (in_mf == 2) {
+      if (x >= q) x -= q;
+    } else if (in_mf == 4) {
+      if (x >= two_q) x -= two_q;
+      if (out_mf == 1 && x >= q) x -= q;
+    }
+    r[i] = x;
+  }
+}
+
+/* hexl/util/util-internal.hpp:16-42, enum values hexl/include/hexl/util/util.hpp:16-25 */
+static inline int cmp_holds(int cmp, uint64_t lhs, uint64_t rhs) {
+  switch (cmp) {
+    case 0: return lhs == rhs; /* EQ  */
+    case 1: return lhs < rhs;  /* LT  */
+    case 2: return lhs <= rhs; /* LE  */
+    case 3: return 0;          /* FALSE */
+    case 4: return lhs != rhs; /* NE  */
+    case 5: return lhs >= rhs; /* NLT */
+    case 6: return lhs > rhs;  /* NLE */
+    default: return 1;         /* TRUE */
+  }
+}
+
+/* hexl/eltwise/eltwise-cmp-add.cpp:32-106: wrapping add, no modulus */
+void orc_eltwise_cmp_add(uint64_t* r, const uint64_t* a, uint64_t n, int cmp, uint64_t bound,
+                         uint64_t diff) {
+  for (uint64_t i = 0; i < n; ++i) r[i] = cmp_holds(cmp, a[i], bound) ? a[i] + diff : a[i];
+}
+
+/* hexl/eltwise/eltwise-cmp-sub-mod.cpp:47-66: compare the RAW operand, reduce it
+ * with a true %, then subtract diff modularly where the comparison held */
+void orc_eltwise_cmp_sub_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_t q, int cmp,
+                             uint64_t bound, uint64_t diff) {
+  for (uint64_t i = 0; i < n; ++i) {
+    int hit = cmp_holds(cmp, a[i], bound);
+    uint64_t x = a[i] % q;
+    r[i] = hit ? orc_sub_mod(x, diff, q) : x;
+  }
+}

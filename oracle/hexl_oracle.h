@@ -1,0 +1,64 @@
+/* TEST INFRASTRUCTURE ONLY -- see hexl_oracle.c.  Parity status: PINNED
+ * (checked against the reference's golden vectors in tests/golden/ and against
+ * oracle/_ref, the compiled reference itself; tests/test_oracle_*.py). */
+#ifndef HEXL_ORACLE_H
+#define HEXL_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* number theory */
+uint64_t orc_multiply_mod(uint64_t x, uint64_t y, uint64_t q);
+uint64_t orc_add_mod(uint64_t x, uint64_t y, uint64_t q);
+uint64_t orc_sub_mod(uint64_t x, uint64_t y, uint64_t q);
+uint64_t orc_pow_mod(uint64_t base, uint64_t exp, uint64_t q);
+uint64_t orc_inverse_mod(uint64_t x, uint64_t q);
+uint64_t orc_reverse_bits(uint64_t x, uint64_t bit_width);
+int orc_is_prime(uint64_t n);
+int orc_is_primitive_root(uint64_t root, uint64_t degree, uint64_t q);
+uint64_t orc_minimal_primitive_root(uint64_t degree, uint64_t q);
+int orc_generate_primes(uint64_t* out, uint64_t num, uint64_t bits, int prefer_small,
+                        uint64_t ntt_size);
+uint64_t orc_multiply_factor(uint64_t operand, unsigned bit_shift, uint64_t q);
+
+/* NTT tables, laid out exactly as the reference's getters return them */
+void orc_ntt_tables(uint64_t n, uint64_t q, uint64_t root, uint64_t* w, uint64_t* w_precon,
+                    uint64_t* inv_w, uint64_t* inv_w_precon);
+
+/* transforms on `batch` back-to-back polynomials; tables from orc_ntt_tables */
+void orc_ntt_forward(uint64_t* result, const uint64_t* operand, uint64_t n, uint64_t q,
+                     const uint64_t* w, const uint64_t* w_precon, uint64_t in_mf,
+                     uint64_t out_mf, uint64_t batch, int threads);
+void orc_ntt_inverse(uint64_t* result, const uint64_t* operand, uint64_t n, uint64_t q,
+                     const uint64_t* inv_w, const uint64_t* inv_w_precon, uint64_t in_mf,
+                     uint64_t out_mf, uint64_t batch, int threads);
+void orc_ntt_forward_textbook(uint64_t* operand, uint64_t n, uint64_t q, const uint64_t* w);
+void orc_ntt_inverse_textbook(uint64_t* operand, uint64_t n, uint64_t q,
+                              const uint64_t* inv_w);
+
+/* element-wise ops */
+void orc_eltwise_add_mod(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t n,
+                         uint64_t q);
+void orc_eltwise_add_mod_scalar(uint64_t* r, const uint64_t* a, uint64_t b, uint64_t n,
+                                uint64_t q);
+void orc_eltwise_sub_mod(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t n,
+                         uint64_t q);
+void orc_eltwise_sub_mod_scalar(uint64_t* r, const uint64_t* a, uint64_t b, uint64_t n,
+                                uint64_t q);
+void orc_eltwise_mult_mod(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t n,
+                          uint64_t q, uint64_t in_mf);
+void orc_eltwise_fma_mod(uint64_t* r, const uint64_t* a, uint64_t b, const uint64_t* c,
+                         uint64_t n, uint64_t q, uint64_t in_mf);
+void orc_eltwise_reduce_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_t q,
+                            uint64_t in_mf, uint64_t out_mf);
+void orc_eltwise_cmp_add(uint64_t* r, const uint64_t* a, uint64_t n, int cmp, uint64_t bound,
+                         uint64_t diff);
+void orc_eltwise_cmp_sub_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_t q, int cmp,
+                             uint64_t bound, uint64_t diff);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,274 @@
+// TEST INFRASTRUCTURE ONLY -- C-callable veneer over the UNMODIFIED reference
+// (intel/hexl v1.2.5 compiled from /root/reference by oracle/Makefile into
+// oracle/_ref/libhexl_ref.so).  Nothing under hexl_b200/ may link or load this.
+//
+// Every entry point forwards to the reference's own public API
+// (hexl/include/hexl/ntt/ntt.hpp:99,109; hexl/include/hexl/eltwise/*.hpp) or, for
+// the "*_native" variants, to the reference's scalar C++ path
+// (hexl/ntt/ntt-internal.hpp:34,98; hexl/eltwise/*-internal.hpp), which is the
+// tier BASELINE.json's north_star names as the bit-exact oracle.
+#include <stdint.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+#include "eltwise/eltwise-add-mod-internal.hpp"
+#include "eltwise/eltwise-cmp-add-internal.hpp"
+#include "eltwise/eltwise-cmp-sub-mod-internal.hpp"
+#include "eltwise/eltwise-fma-mod-internal.hpp"
+#include "eltwise/eltwise-mult-mod-internal.hpp"
+#include "eltwise/eltwise-reduce-mod-internal.hpp"
+#include "eltwise/eltwise-sub-mod-internal.hpp"
+#include "hexl/eltwise/eltwise-add-mod.hpp"
+#include "hexl/eltwise/eltwise-cmp-add.hpp"
+#include "hexl/eltwise/eltwise-cmp-sub-mod.hpp"
+#include "hexl/eltwise/eltwise-fma-mod.hpp"
+#include "hexl/eltwise/eltwise-mult-mod.hpp"
+#include "hexl/eltwise/eltwise-reduce-mod.hpp"
+#include "hexl/eltwise/eltwise-sub-mod.hpp"
+#include "hexl/ntt/ntt.hpp"
+#include "hexl/number-theory/number-theory.hpp"
+#include "hexl/util/util.hpp"
+#include "ntt/ntt-internal.hpp"
+#include "util/cpu-features.hpp"
+
+using namespace intel::hexl;
+
+namespace {
+template <class F>
+void parallel_units(uint64_t units, int threads, F&& body) {
+  if (threads <= 1 || units <= 1) {
+    for (uint64_t u = 0; u < units; ++u) body(u);
+    return;
+  }
+  int nt = static_cast<int>(std::min<uint64_t>(threads, units));
+  std::vector<std::thread> pool;
+  pool.reserve(nt);
+  for (int t = 0; t < nt; ++t) {
+    pool.emplace_back([=, &body]() {
+      // contiguous block split, one polynomial per call (README.md:264-265:
+      // the library is single-threaded and thread-safe)
+      uint64_t lo = units * t / nt, hi = units * (t + 1) / nt;
+      for (uint64_t u = lo; u < hi; ++u) body(u);
+    });
+  }
+  for (auto& th : pool) th.join();
+}
+}  // namespace
+
+extern "C" {
+
+// ---- which tier the reference will dispatch on this host ---------------------
+int ref_has_avx512dq() { return has_avx512dq ? 1 : 0; }
+int ref_has_avx512ifma() { return has_avx512ifma ? 1 : 0; }
+
+// ---- number theory ---------------------------------------------------------
+uint64_t ref_minimal_primitive_root(uint64_t degree, uint64_t q) {
+  return MinimalPrimitiveRoot(degree, q);
+}
+int ref_is_prime(uint64_t n) { return IsPrime(n) ? 1 : 0; }
+int ref_generate_primes(uint64_t* out, uint64_t num, uint64_t bits,
+                        int prefer_small, uint64_t ntt_size) {
+  std::vector<uint64_t> p = GeneratePrimes(num, bits, prefer_small != 0, ntt_size);
+  for (size_t i = 0; i < p.size() && i < num; ++i) out[i] = p[i];
+  return static_cast<int>(p.size());
+}
+uint64_t ref_inverse_mod(uint64_t x, uint64_t q) { return InverseMod(x, q); }
+uint64_t ref_pow_mod(uint64_t b, uint64_t e, uint64_t q) { return PowMod(b, e, q); }
+uint64_t ref_multiply_mod(uint64_t x, uint64_t y, uint64_t q) {
+  return MultiplyMod(x, y, q);
+}
+uint64_t ref_reverse_bits(uint64_t x, uint64_t w) { return ReverseBits(x, w); }
+
+// ---- NTT object --------------------------------------------------------------
+void* ref_ntt_create(uint64_t n, uint64_t q) { return new NTT(n, q); }
+void* ref_ntt_create_root(uint64_t n, uint64_t q, uint64_t root) {
+  return new NTT(n, q, root);
+}
+void ref_ntt_destroy(void* h) { delete static_cast<NTT*>(h); }
+uint64_t ref_ntt_root(void* h) {
+  return static_cast<NTT*>(h)->GetMinimalRootOfUnity();
+}
+void ref_ntt_tables(void* h, uint64_t* w, uint64_t* w_precon64, uint64_t* inv_w,
+                    uint64_t* inv_w_precon64) {
+  NTT* t = static_cast<NTT*>(h);
+  uint64_t n = t->GetDegree();
+  if (w) std::copy_n(t->GetRootOfUnityPowers().data(), n, w);
+  if (w_precon64) std::copy_n(t->GetPrecon64RootOfUnityPowers().data(), n, w_precon64);
+  if (inv_w) std::copy_n(t->GetInvRootOfUnityPowers().data(), n, inv_w);
+  if (inv_w_precon64)
+    std::copy_n(t->GetPrecon64InvRootOfUnityPowers().data(), n, inv_w_precon64);
+}
+
+// public-API dispatch (AVX-512 when the host has it), `batch` polynomials of
+// degree n laid out back to back, `threads` host threads.
+void ref_ntt_forward(void* h, uint64_t* result, const uint64_t* operand,
+                     uint64_t in_mf, uint64_t out_mf, uint64_t batch, int threads) {
+  NTT* t = static_cast<NTT*>(h);
+  uint64_t n = t->GetDegree();
+  parallel_units(batch, threads, [&](uint64_t u) {
+    t->ComputeForward(result + u * n, operand + u * n, in_mf, out_mf);
+  });
+}
+void ref_ntt_inverse(void* h, uint64_t* result, const uint64_t* operand,
+                     uint64_t in_mf, uint64_t out_mf, uint64_t batch, int threads) {
+  NTT* t = static_cast<NTT*>(h);
+  uint64_t n = t->GetDegree();
+  parallel_units(batch, threads, [&](uint64_t u) {
+    t->ComputeInverse(result + u * n, operand + u * n, in_mf, out_mf);
+  });
+}
+
+// scalar ("native C++") tier, reached directly
+void ref_ntt_forward_native(void* h, uint64_t* result, const uint64_t* operand,
+                            uint64_t in_mf, uint64_t out_mf, uint64_t batch,
+                            int threads) {
+  NTT* t = static_cast<NTT*>(h);
+  uint64_t n = t->GetDegree();
+  parallel_units(batch, threads, [&](uint64_t u) {
+    ForwardTransformToBitReverseRadix2(
+        result + u * n, operand + u * n, n, t->GetModulus(),
+        t->GetRootOfUnityPowers().data(), t->GetPrecon64RootOfUnityPowers().data(),
+        in_mf, out_mf);
+  });
+}
+void ref_ntt_inverse_native(void* h, uint64_t* result, const uint64_t* operand,
+                            uint64_t in_mf, uint64_t out_mf, uint64_t batch,
+                            int threads) {
+  NTT* t = static_cast<NTT*>(h);
+  uint64_t n = t->GetDegree();
+  parallel_units(batch, threads, [&](uint64_t u) {
+    InverseTransformFromBitReverseRadix2(
+        result + u * n, operand + u * n, n, t->GetModulus(),
+        t->GetInvRootOfUnityPowers().data(),
+        t->GetPrecon64InvRootOfUnityPowers().data(), in_mf, out_mf);
+  });
+}
+// textbook O(N log N) transforms the reference's own tests use as ground truth
+// (hexl/ntt/ntt-radix-2.cpp:263-328); in place.
+void ref_ntt_forward_textbook(void* h, uint64_t* operand) {
+  NTT* t = static_cast<NTT*>(h);
+  ReferenceForwardTransformToBitReverse(operand, t->GetDegree(), t->GetModulus(),
+                                        t->GetRootOfUnityPowers().data());
+}
+void ref_ntt_inverse_textbook(void* h, uint64_t* operand) {
+  NTT* t = static_cast<NTT*>(h);
+  ReferenceInverseTransformFromBitReverse(operand, t->GetDegree(), t->GetModulus(),
+                                          t->GetInvRootOfUnityPowers().data());
+}
+void ref_ntt_forward_radix4(void* h, uint64_t* result, const uint64_t* operand,
+                            uint64_t in_mf, uint64_t out_mf) {
+  NTT* t = static_cast<NTT*>(h);
+  ForwardTransformToBitReverseRadix4(
+      result, operand, t->GetDegree(), t->GetModulus(),
+      t->GetRootOfUnityPowers().data(), t->GetPrecon64RootOfUnityPowers().data(),
+      in_mf, out_mf);
+}
+void ref_ntt_inverse_radix4(void* h, uint64_t* result, const uint64_t* operand,
+                            uint64_t in_mf, uint64_t out_mf) {
+  NTT* t = static_cast<NTT*>(h);
+  InverseTransformFromBitReverseRadix4(
+      result, operand, t->GetDegree(), t->GetModulus(),
+      t->GetInvRootOfUnityPowers().data(),
+      t->GetPrecon64InvRootOfUnityPowers().data(), in_mf, out_mf);
+}
+
+// ---- eltwise, public dispatch; `batch` rows of n elements, `threads` threads ---
+#define ROWS(expr)                                        \
+  parallel_units(batch, threads, [&](uint64_t u) {        \
+    const uint64_t o = u * n;                             \
+    (void)o;                                              \
+    expr;                                                 \
+  })
+
+void ref_eltwise_add_mod(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t n,
+                         uint64_t q, uint64_t batch, int threads) {
+  ROWS(EltwiseAddMod(r + o, a + o, b + o, n, q));
+}
+void ref_eltwise_add_mod_scalar(uint64_t* r, const uint64_t* a, uint64_t b, uint64_t n,
+                                uint64_t q, uint64_t batch, int threads) {
+  ROWS(EltwiseAddMod(r + o, a + o, b, n, q));
+}
+void ref_eltwise_sub_mod(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t n,
+                         uint64_t q, uint64_t batch, int threads) {
+  ROWS(EltwiseSubMod(r + o, a + o, b + o, n, q));
+}
+void ref_eltwise_sub_mod_scalar(uint64_t* r, const uint64_t* a, uint64_t b, uint64_t n,
+                                uint64_t q, uint64_t batch, int threads) {
+  ROWS(EltwiseSubMod(r + o, a + o, b, n, q));
+}
+void ref_eltwise_mult_mod(uint64_t* r, const uint64_t* a, const uint64_t* b, uint64_t n,
+                          uint64_t q, uint64_t in_mf, uint64_t batch, int threads) {
+  ROWS(EltwiseMultMod(r + o, a + o, b + o, n, q, in_mf));
+}
+void ref_eltwise_fma_mod(uint64_t* r, const uint64_t* a, uint64_t b, const uint64_t* c,
+                         uint64_t n, uint64_t q, uint64_t in_mf, uint64_t batch,
+                         int threads) {
+  ROWS(EltwiseFMAMod(r + o, a + o, b, c ? c + o : nullptr, n, q, in_mf));
+}
+void ref_eltwise_reduce_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_t q,
+                            uint64_t in_mf, uint64_t out_mf, uint64_t batch,
+                            int threads) {
+  ROWS(EltwiseReduceMod(r + o, a + o, n, q, in_mf, out_mf));
+}
+void ref_eltwise_cmp_add(uint64_t* r, const uint64_t* a, uint64_t n, int cmp,
+                         uint64_t bound, uint64_t diff, uint64_t batch, int threads) {
+  ROWS(EltwiseCmpAdd(r + o, a + o, n, static_cast<CMPINT>(cmp), bound, diff));
+}
+void ref_eltwise_cmp_sub_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_t q,
+                             int cmp, uint64_t bound, uint64_t diff, uint64_t batch,
+                             int threads) {
+  ROWS(EltwiseCmpSubMod(r + o, a + o, n, q, static_cast<CMPINT>(cmp), bound, diff));
+}
+
+// ---- eltwise, scalar ("native") tier ------------------------------------------
+void ref_eltwise_add_mod_native(uint64_t* r, const uint64_t* a, const uint64_t* b,
+                                uint64_t n, uint64_t q) {
+  EltwiseAddModNative(r, a, b, n, q);
+}
+void ref_eltwise_add_mod_scalar_native(uint64_t* r, const uint64_t* a, uint64_t b,
+                                       uint64_t n, uint64_t q) {
+  EltwiseAddModNative(r, a, b, n, q);
+}
+void ref_eltwise_sub_mod_native(uint64_t* r, const uint64_t* a, const uint64_t* b,
+                                uint64_t n, uint64_t q) {
+  EltwiseSubModNative(r, a, b, n, q);
+}
+void ref_eltwise_sub_mod_scalar_native(uint64_t* r, const uint64_t* a, uint64_t b,
+                                       uint64_t n, uint64_t q) {
+  EltwiseSubModNative(r, a, b, n, q);
+}
+void ref_eltwise_mult_mod_native(uint64_t* r, const uint64_t* a, const uint64_t* b,
+                                 uint64_t n, uint64_t q, uint64_t in_mf) {
+  switch (in_mf) {
+    case 1: EltwiseMultModNative<1>(r, a, b, n, q); break;
+    case 2: EltwiseMultModNative<2>(r, a, b, n, q); break;
+    default: EltwiseMultModNative<4>(r, a, b, n, q); break;
+  }
+}
+void ref_eltwise_fma_mod_native(uint64_t* r, const uint64_t* a, uint64_t b,
+                                const uint64_t* c, uint64_t n, uint64_t q,
+                                uint64_t in_mf) {
+  switch (in_mf) {
+    case 1: EltwiseFMAModNative<1>(r, a, b, c, n, q); break;
+    case 2: EltwiseFMAModNative<2>(r, a, b, c, n, q); break;
+    case 4: EltwiseFMAModNative<4>(r, a, b, c, n, q); break;
+    default: EltwiseFMAModNative<8>(r, a, b, c, n, q); break;
+  }
+}
+void ref_eltwise_reduce_mod_native(uint64_t* r, const uint64_t* a, uint64_t n,
+                                   uint64_t q, uint64_t in_mf, uint64_t out_mf) {
+  EltwiseReduceModNative(r, a, n, q, in_mf, out_mf);
+}
+void ref_eltwise_cmp_add_native(uint64_t* r, const uint64_t* a, uint64_t n, int cmp,
+                                uint64_t bound, uint64_t diff) {
+  EltwiseCmpAddNative(r, a, n, static_cast<CMPINT>(cmp), bound, diff);
+}
+void ref_eltwise_cmp_sub_mod_native(uint64_t* r, const uint64_t* a, uint64_t n,
+                                    uint64_t q, int cmp, uint64_t bound,
+                                    uint64_t diff) {
+  EltwiseCmpSubModNative(r, a, n, q, static_cast<CMPINT>(cmp), bound, diff);
+}
+
+}  // extern "C"

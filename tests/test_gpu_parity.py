@@ -1,0 +1,354 @@
+"""Parity of the sm_100a path against the oracle, through the C ABI.
+
+Bar: bit-exact for every canonical output (NTT out_mf == 1, every eltwise op);
+for the lazy outputs (forward out_mf == 4, inverse out_mf == 2, ReduceMod q->2)
+congruent mod q and inside the advertised range -- the reference's own tests
+compare lazy outputs only mod q (test/test-ntt.cpp:246-251,279-286) because its
+tiers disagree bit-wise there.  The checker is the compiled reference when
+oracle/_ref travelled with the repo, else the C restatement.
+"""
+import numpy as np
+import pytest
+
+from util import kat_modulus, kat_values, uniform_below
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda(hb):
+    if not torch.cuda.is_available() or hb.device_count() == 0:
+        pytest.fail("gpu-marked test collected on a machine without CUDA")
+
+
+# ---------------------------------------------------------------- NTT: KATs
+def test_ntt_reference_kats(hb, kats):
+    """test/test-ntt.cpp:231-355 on the 14 tuples of :357-404, device and host buffers."""
+    for c in kats["ntt_forward"]["cases"]:
+        n, q = c["n"], c["q"]
+        x = np.array(c["input"], dtype=np.uint64)
+        exp = np.array(c["output"], dtype=np.uint64)
+        t = hb.NTT(n, q)
+        # in-place forward on the device
+        d = dev(x)
+        t.ComputeForward(d, d, 1, 1)
+        assert (host(d) == exp).all(), c
+        # lazy forward, compared mod q
+        d = dev(x)
+        t.ComputeForward(d, d, 2, 4)
+        assert (host(d) % np.uint64(q) == exp).all() and (host(d) < np.uint64(4 * q)).all(), c
+        # out of place + round trip
+        o, d = dev(np.zeros_like(x)), dev(x)
+        t.ComputeForward(o, d, 2, 1)
+        assert (host(o) == exp).all() and (host(d) == x).all()
+        t.ComputeInverse(d, o, 1, 1)
+        assert (host(d) == x).all()
+        t.ComputeInverse(d, o, 1, 2)
+        assert (host(d) % np.uint64(q) == x).all() and (host(d) < np.uint64(2 * q)).all()
+        # host-pointer path (what an unmodified caller of the reference API uses)
+        y = np.zeros_like(x)
+        t.ComputeForward(y, x, 1, 1)
+        assert (y == exp).all()
+        t.ComputeInverse(y, y, 1, 1)
+        assert (y == x).all()
+
+
+# ------------------------------------------- NTT: every size against the oracle
+SIZES = [(1, 48), (2, 20), (3, 22), (4, 29), (5, 31), (6, 33), (7, 40), (8, 48), (9, 49), (10, 30),
+         (10, 61), (11, 50), (12, 51), (12, 61), (13, 58), (13, 30), (14, 59), (14, 61), (15, 50), (16, 55),
+         (16, 61), (17, 60), (17, 61)]
+
+
+@pytest.mark.parametrize("logn,bits", SIZES)
+def test_ntt_matches_oracle(hb, checker, logn, bits):
+    n = 1 << logn
+    q = hb.GeneratePrimes(1, bits, True, n)[0]
+    qq = np.uint64(q)
+    t = hb.NTT(n, q)
+    batch = max(1, min(37, (1 << 16) // n))  # ragged batch: not a multiple of the CTA packing
+    for in_mf, out_mf in [(1, 1), (4, 1), (2, 4)]:
+        x = uniform_below(logn * 10 + in_mf, n * batch, q * in_mf)
+        exp = checker.ntt_forward(x, n, q, in_mf, 1)
+        o = dev(np.zeros_like(x))
+        t.ComputeForward(o, dev(x), in_mf, out_mf)
+        got = host(o)
+        if out_mf == 1:
+            assert (got == exp).all(), (logn, in_mf, out_mf, int((got != exp).sum()))
+        else:
+            assert (got % qq == exp).all() and (got < np.uint64(4 * q)).all()
+    for in_mf, out_mf in [(1, 1), (2, 1), (2, 2)]:
+        x = uniform_below(logn * 20 + in_mf, n * batch, q * in_mf)
+        exp = checker.ntt_inverse(x, n, q, in_mf, 1)
+        o = dev(np.zeros_like(x))
+        t.ComputeInverse(o, dev(x), in_mf, out_mf)
+        got = host(o)
+        if out_mf == 1:
+            assert (got == exp).all(), (logn, in_mf, out_mf, int((got != exp).sum()))
+        else:
+            assert (got % qq == exp).all() and (got < np.uint64(2 * q)).all()
+    # in place, device
+    x = uniform_below(logn, n * batch, q)
+    d = dev(x)
+    t.ComputeForward(d, d, 1, 1)
+    assert (host(d) == checker.ntt_forward(x, n, q)).all()
+    t.ComputeInverse(d, d, 1, 1)
+    assert (host(d) == x).all()
+
+
+def test_ntt_extreme_inputs(hb, checker):
+    """all-zero, all q-1, and lazy inputs at the top of their range (4q-1 / 2q-1),
+    at the largest supported modulus size (q just below 2^62)."""
+    for logn in (4, 10, 12, 15):
+        n = 1 << logn
+        q = hb.GeneratePrimes(1, 61, False, n)[0]  # largest primes below 2^62
+        assert q < (1 << 62)
+        t = hb.NTT(n, q)
+        for fill, in_mf in [(0, 1), (q - 1, 1), (4 * q - 1, 4), (2 * q - 1, 2)]:
+            x = np.full(n, fill, dtype=np.uint64)
+            o = dev(np.zeros_like(x))
+            t.ComputeForward(o, dev(x), in_mf, 1)
+            assert (host(o) == checker.ntt_forward(x, n, q, in_mf, 1)).all(), (logn, fill)
+            if in_mf <= 2:
+                t.ComputeInverse(o, dev(x), in_mf, 1)
+                assert (host(o) == checker.ntt_inverse(x, n, q, in_mf, 1)).all(), (logn, fill)
+
+
+def test_ntt_user_root(hb, checker):
+    n = 256
+    q = hb.GeneratePrimes(1, 40, True, n)[0]
+    root = hb.PowMod(hb.MinimalPrimitiveRoot(2 * n, q), 5, q)
+    t = hb.NTT(n, q, root)
+    x = uniform_below(5, n, q)
+    o = dev(np.zeros_like(x))
+    t.ComputeForward(o, dev(x), 1, 1)
+    assert (host(o) == checker.ntt_forward(x, n, q, 1, 1, root=root)).all()
+
+
+def test_ntt_linearity_and_roundtrip_full_size(hb):
+    """Size-independent properties at BASELINE's N = 2^16 / 55-bit, on a batch
+    large enough to span many waves: Inv(Fwd(x)) == x, and Fwd is linear."""
+    n = 1 << 16
+    q = hb.GeneratePrimes(1, 55, True, n)[0]
+    t = hb.NTT(n, q)
+    batch = 512
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randint(0, q, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    b = torch.randint(0, q, (batch, n), dtype=torch.int64, device="cuda", generator=g)
+    fa, fb, fs = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+    s = torch.empty_like(a)
+    hb.EltwiseAddMod(s, a, b, a.numel(), q)
+    t.ComputeForward(fa, a, 1, 1)
+    t.ComputeForward(fb, b, 1, 1)
+    t.ComputeForward(fs, s, 1, 1)
+    hb.EltwiseAddMod(fa, fa, fb, a.numel(), q)
+    assert torch.equal(fa, fs)
+    t.ComputeInverse(fs, fs, 1, 1)
+    assert torch.equal(fs, s)
+    assert int(fs.max()) < q and int(fs.min()) >= 0
+
+
+def test_ntt_host_pointer_batches(hb, checker):
+    """host buffers, batch spanning several staging chunks, pinned and pageable"""
+    n = 1 << 12
+    q = hb.GeneratePrimes(1, 50, True, n)[0]
+    t = hb.NTT(n, q)
+    batch = 3000  # 96 MB > 32 MiB chunks x 3 slots
+    x = uniform_below(77, n * batch, q)
+    exp = checker.ntt_forward(x, n, q)
+    y = np.zeros_like(x)
+    t.ComputeForward(y, x, 1, 1)
+    assert (y == exp).all()
+    px = hb.pinned_empty(n * batch)
+    px[:] = x
+    t.ComputeForward(px, px, 1, 1)
+    assert (px == exp).all()
+    t.ComputeInverse(px, px, 1, 1)
+    assert (px == x).all()
+    hb.pinned_free(px)
+
+
+def test_mixed_pointers_rejected(hb):
+    t = hb.NTT(16, hb.GeneratePrimes(1, 30, True, 16)[0])
+    x = np.zeros(16, dtype=np.uint64)
+    with pytest.raises(hb.HexlB200Error) as ei:
+        t.ComputeForward(dev(x), x, 1, 1)
+    assert ei.value.code == -5
+
+
+def test_debug_bounds_checks(hb):
+    """HEXL_DEBUG-style range checks (check.hpp:33-36; test-eltwise-mult-mod.cpp:66-76)"""
+    hb.set_debug(True)
+    try:
+        q = 769
+        t = hb.NTT(8, q)
+        bad = dev(np.array([0, 1, 2, 3, 4, 5, 6, 770], dtype=np.uint64))
+        good = dev(np.arange(8, dtype=np.uint64))
+        with pytest.raises(hb.HexlB200Error):
+            t.ComputeForward(good.clone(), bad, 1, 1)
+        t.ComputeForward(good.clone(), bad, 2, 1)  # 770 < 2q is fine
+        with pytest.raises(hb.HexlB200Error):
+            hb.EltwiseMultMod(good.clone(), good, bad, 8, q, 1)
+        with pytest.raises(hb.HexlB200Error):
+            hb.EltwiseAddMod(good.clone(), bad, good, 8, q)
+        with pytest.raises(hb.HexlB200Error):
+            hb.EltwiseFMAMod(np.zeros(8, dtype=np.uint64), host(bad), 1, None, 8, q, 1)
+    finally:
+        hb.set_debug(False)
+
+
+# ------------------------------------------------------------- eltwise: KATs
+def test_eltwise_reference_kats(hb, kats):
+    gp = hb.GeneratePrimes
+    for c in kats["eltwise_mult_mod"]["cases"]:
+        q = kat_modulus(c["q"], gp)
+        a, b = kat_values(c["op1"], q), kat_values(c["op2"], q)
+        d = dev(a)
+        hb.EltwiseMultMod(d, d, dev(b), len(a), q, c["in_mf"])  # in place, as the reference tests
+        assert (host(d) == kat_values(c["out"], q)).all(), c
+        r = np.zeros_like(a)
+        hb.EltwiseMultMod(r, a, b, len(a), q, c["in_mf"])  # host pointers
+        assert (r == kat_values(c["out"], q)).all(), c
+    for c in kats["eltwise_fma_mod"]["cases"]:
+        q = c["q"]
+        a1 = kat_values(c["arg1"], q)
+        a3 = None if c["arg3"] is None else dev(kat_values(c["arg3"], q))
+        d = dev(a1)
+        hb.EltwiseFMAMod(d, d, c["arg2"], a3, len(a1), q, c["in_mf"])
+        assert (host(d) == kat_values(c["out"], q)).all(), c
+    s = kats["eltwise_fma_mod"]["in_mf_sweep"]
+    for mf in s["in_mfs"]:
+        q = s["q"]
+        a1 = kat_values(s["arg1_base"], q) + np.uint64((mf - 1) * q)
+        d = dev(a1)
+        hb.EltwiseFMAMod(d, d, s["arg2"], dev(kat_values(s["arg3"], q)), len(a1), q, mf)
+        assert (host(d) == kat_values(s["out"], q)).all(), mf
+    for c in kats["eltwise_reduce_mod"]["cases"]:
+        q = c["q"]
+        in_mf = q if c["in_mf"] == "q" else c["in_mf"]
+        op = kat_values(c["op"], q)
+        r = dev(np.zeros_like(op))
+        hb.EltwiseReduceMod(r, dev(op), len(op), q, in_mf, c["out_mf"])
+        assert (host(r) == kat_values(c["out"], q)).all(), c
+    for name, fn in (("eltwise_add_mod", hb.EltwiseAddMod), ("eltwise_sub_mod", hb.EltwiseSubMod)):
+        for c in kats[name]["cases"]:
+            q = kat_modulus(c["q"], gp)
+            a, b = kat_values(c["op1"], q), kat_values(c["op2"], q)
+            d = dev(a)
+            fn(d, d, b if isinstance(b, int) else dev(b), len(a), q)
+            assert (host(d) == kat_values(c["out"], q)).all(), c
+    for c in kats["eltwise_cmp_add"]["cases"]:
+        a = kat_values(c["op1"], 0)
+        d = dev(a)
+        hb.EltwiseCmpAdd(d, d, len(a), c["cmp"], c["bound"], c["diff"])
+        assert (host(d) == kat_values(c["out"], 0)).all()
+    for c in kats["eltwise_cmp_sub_mod"]["cases"]:
+        a = kat_values(c["op1"], 0)
+        d = dev(a)
+        hb.EltwiseCmpSubMod(d, d, len(a), c["q"], c["cmp"], c["bound"], c["diff"])
+        assert (host(d) == kat_values(c["out"], 0)).all()
+
+
+# ------------------------------------------------ eltwise: random vs the oracle
+@pytest.mark.parametrize("bits", [20, 30, 32, 40, 50, 55, 59, 60])
+@pytest.mark.parametrize("n", [1, 7, 1024 + 7, 1 << 16])
+def test_eltwise_matches_oracle(hb, checker, bits, n):
+    q = hb.GeneratePrimes(1, bits, True, 1)[0]
+    qq = np.uint64(q)
+    a, b = uniform_below(1, n, q), uniform_below(2, n, q)
+    da, db = dev(a), dev(b)
+    r = torch.empty_like(da)
+    assert (host(hb.EltwiseAddMod(r, da, db, n, q)) == checker.add_mod(a, b, q)).all()
+    assert (host(hb.EltwiseAddMod(r, da, int(b[0]), n, q)) == checker.add_mod(a, int(b[0]), q)).all()
+    assert (host(hb.EltwiseSubMod(r, da, db, n, q)) == checker.sub_mod(a, b, q)).all()
+    assert (host(hb.EltwiseSubMod(r, da, int(b[0]), n, q)) == checker.sub_mod(a, int(b[0]), q)).all()
+    for mf in (1, 2, 4):
+        x, y = uniform_below(3, n, mf * q), uniform_below(4, n, mf * q)
+        assert (host(hb.EltwiseMultMod(r, dev(x), dev(y), n, q, mf)) == checker.mult_mod(x, y, q, mf)).all()
+    for mf in (1, 2, 4, 8):
+        x, c = uniform_below(5, n, mf * q), uniform_below(6, n, mf * q)
+        s = int(uniform_below(7, 1, mf * q)[0])
+        assert (host(hb.EltwiseFMAMod(r, dev(x), s, dev(c), n, q, mf)) == checker.fma_mod(x, s, c, q, mf)).all()
+        assert (host(hb.EltwiseFMAMod(r, dev(x), s, None, n, q, mf)) == checker.fma_mod(x, s, None, q, mf)).all()
+    wide = uniform_below(8, n, 1 << 64)
+    assert (host(hb.EltwiseReduceMod(r, dev(wide), n, q, q, 1)) == wide % qq).all()
+    lazy = host(hb.EltwiseReduceMod(r, dev(wide), n, q, q, 2))
+    assert (lazy % qq == wide % qq).all() and (lazy < np.uint64(2 * q)).all()
+    x4 = uniform_below(9, n, 4 * q)
+    assert (host(hb.EltwiseReduceMod(r, dev(x4), n, q, 4, 1)) == checker.reduce_mod(x4, q, 4, 1)).all()
+    assert (host(hb.EltwiseReduceMod(r, dev(x4), n, q, 4, 2)) == checker.reduce_mod(x4, q, 4, 2)).all()
+    x2 = uniform_below(10, n, 2 * q)
+    assert (host(hb.EltwiseReduceMod(r, dev(x2), n, q, 2, 1)) == checker.reduce_mod(x2, q, 2, 1)).all()
+    assert (host(hb.EltwiseReduceMod(r, dev(x2), n, q, 2, 2)) == x2).all()  # equal factors: copy
+    w = uniform_below(11, n, 1 << 64)
+    diff = int(b[n // 2]) or 1
+    for cmp in range(8):
+        bound = int(w[n // 3])
+        assert (host(hb.EltwiseCmpAdd(r, dev(w), n, cmp, bound, diff)) == checker.cmp_add(w, cmp, bound, diff)).all()
+        assert (host(hb.EltwiseCmpSubMod(r, dev(w), n, q, cmp, bound, diff))
+                == checker.cmp_sub_mod(w, q, cmp, bound, diff)).all()
+
+
+def test_eltwise_unaligned_and_inplace(hb, checker):
+    """operands at odd 8-byte offsets take the scalar instantiation; in-place aliasing"""
+    q = hb.GeneratePrimes(1, 55, True, 1)[0]
+    n = 4099
+    a, b = uniform_below(1, n + 1, q), uniform_below(2, n + 1, q)
+    da, db = dev(a), dev(b)
+    ra = da[1:]  # 8-byte aligned only
+    hb.EltwiseMultMod(ra, ra, db[1:], n, q, 1)
+    assert (host(da)[1:] == checker.mult_mod(a[1:], b[1:], q, 1)).all() and host(da)[0] == a[0]
+    da = dev(a)
+    hb.EltwiseFMAMod(da[:n], da[:n], 12345, db[1:], n, q, 1)
+    assert (host(da)[:n] == checker.fma_mod(a[:n], 12345, b[1:], q, 1)).all()
+
+
+def test_eltwise_host_pointers_large(hb, checker):
+    q = hb.GeneratePrimes(1, 60, True, 1)[0]
+    n = (40 << 20) // 8 * 3 + 5  # several staging chunks plus a ragged tail
+    a, b = uniform_below(1, n, q), uniform_below(2, n, q)
+    r = np.zeros_like(a)
+    hb.EltwiseMultMod(r, a, b, n, q, 1)
+    assert (r == checker.mult_mod(a, b, q, 1)).all()
+    hb.EltwiseFMAMod(r, a, 987654321, b, n, q, 1)
+    assert (r == checker.fma_mod(a, 987654321, b, q, 1)).all()
+    hb.EltwiseReduceMod(r, a, n, q, q, 1)
+    assert (r == a).all()
+
+
+def test_polynomial_product_pipeline(hb):
+    """FwdNTT -> EltwiseMultMod -> InvNTT equals the schoolbook negacyclic product
+    (the shape of BASELINE config 4), lazy factors (4 on the forward outputs) included."""
+    n = 64
+    q = hb.GeneratePrimes(1, 50, True, n)[0]
+    t = hb.NTT(n, q)
+    a, b = uniform_below(1, n, q), uniform_below(2, n, q)
+    exp = [0] * n
+    for i in range(n):
+        for j in range(n):
+            k, v = (i + j) % n, int(a[i]) * int(b[j])
+            exp[k] = (exp[k] + (v if i + j < n else -v)) % q
+    da, db = dev(a), dev(b)
+    t.ComputeForward(da, da, 1, 4)
+    t.ComputeForward(db, db, 1, 4)
+    hb.EltwiseMultMod(da, da, db, n, q, 4)
+    t.ComputeInverse(da, da, 1, 1)
+    assert [int(v) for v in host(da)] == exp
+
+
+def test_kernels_really_launch(hb):
+    before = hb.launch_count()
+    q = hb.GeneratePrimes(1, 30, True, 1024)[0]
+    d = dev(uniform_below(1, 1024, q))
+    hb.NTT(1024, q).ComputeForward(d, d, 1, 1)
+    torch.cuda.synchronize()
+    assert hb.launch_count() > before

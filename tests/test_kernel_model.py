@@ -1,0 +1,61 @@
+"""Host-logic test of the CUDA kernels' index arithmetic (no GPU): the numpy
+model in tests/kernel_model.py uses the same register/shared-memory/twiddle-node
+formulas as hexl_b200/csrc/ntt.cu and must reproduce the oracle's transform for
+every row length and column-pass split, with permutation-valid and
+bank-conflict-free shared-memory maps."""
+import numpy as np
+import pytest
+
+from kernel_model import Model, plan_col_passes
+from util import uniform_below
+
+
+def build_model(port, n, q):
+    _, w, _, iw, _ = port.tables(n, q)
+    inv = [0] * n
+    inv[0] = int(iw[0])
+    pos, m = 1, n >> 1
+    while m > 0:  # undo the reference's stage-sequential re-ordering
+        for i in range(m):
+            inv[m + i] = int(iw[pos])
+            pos += 1
+        m >>= 1
+    inv_n = pow(n, -1, q)
+    return Model(n, q, [int(v) for v in w], inv, inv_n, (inv_n * inv[1]) % q)
+
+
+@pytest.mark.parametrize("logn,logc", [(4, 4), (5, 5), (6, 6), (7, 7), (8, 8), (9, 9), (10, 10), (11, 11),
+                                       (12, 12), (13, 13), (8, 4), (10, 6), (12, 7), (13, 12), (13, 9),
+                                       (14, 12), (14, 4), (15, 12)])
+def test_model_matches_oracle(port, logn, logc):
+    n = 1 << logn
+    q = port.generate_primes(1, 28, True, n)[0]
+    m = build_model(port, n, q)
+    x = uniform_below(logn * 100 + logc, n, q)
+    y = port.ntt_forward(x, n, q)
+    assert [int(v) for v in m.forward(x, logc)] == [int(v) for v in y]
+    assert [int(v) for v in m.inverse(y, logc)] == [int(v) for v in x]
+
+
+def test_col_pass_plan():
+    assert plan_col_passes(0) == []
+    assert plan_col_passes(4) == [4]
+    assert plan_col_passes(5) == [5]
+    assert plan_col_passes(6) == [3, 3]
+    assert plan_col_passes(8) == [4, 4]
+    for top in range(1, 17):
+        p = plan_col_passes(top)
+        assert sum(p) == top and max(p) <= 5
+
+
+@pytest.mark.parametrize("logc", range(8, 15))
+def test_shared_memory_maps_conflict_free(logc):
+    u = np.arange((1 << logc) // 16)
+    lbs = {logc - 4, 0}
+    p = 1
+    while logc - 4 * p - 1 >= 0:
+        lbs.add(max(logc - 4 * p - 4, 0))
+        p += 1
+    for lb in lbs:
+        for e in range(16):
+            assert Model.bank_conflict_degree(u, e, lb) == 1
