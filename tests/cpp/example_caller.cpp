@@ -1,0 +1,129 @@
+// A reference-style caller: written against the intel::hexl public API only
+// (the scenarios of the reference's example/example.cpp:27-144 plus the NTT
+// allocator/copy semantics of test/test-ntt.cpp:117-200), compiled against
+// include/hexl/hexl.hpp and linked to libhexl_b200.so.  With a GPU it runs and
+// checks the known answers; tests/test_host_api.py at least compiles and links it.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "hexl/hexl.hpp"
+
+using namespace intel::hexl;
+
+static int failures = 0;
+static void Expect(const std::vector<uint64_t>& got, const std::vector<uint64_t>& want, const char* what) {
+  if (got != want) {
+    std::printf("MISMATCH in %s\n", what);
+    ++failures;
+  }
+}
+
+struct CountingAllocator {
+  void* get(size_t bytes) {
+    ++allocations;
+    return std::malloc(bytes);
+  }
+  void put(void* p) { std::free(p); }
+  static size_t allocations;
+};
+size_t CountingAllocator::allocations = 0;
+
+namespace intel {
+namespace hexl {
+template <>
+struct NTT::AllocatorAdapter<CountingAllocator> : public AllocatorInterface<NTT::AllocatorAdapter<CountingAllocator>> {
+  explicit AllocatorAdapter(CountingAllocator&& a_) : a(std::move(a_)) {}
+  void* allocate(size_t bytes_count) { return a.get(bytes_count); }
+  void deallocate(void* p, size_t) { a.put(p); }
+  CountingAllocator a;
+};
+}  // namespace hexl
+}  // namespace intel
+
+int main(int argc, char** argv) {
+  const bool run = argc > 1;  // without arguments: link check + host-only API
+  // host-side API (no GPU needed)
+  if (MinimalPrimitiveRoot(8, 1234565441ULL) != 249725733ULL) ++failures;
+  if (GeneratePrimes(1, 60, true, 1024).size() != 1) ++failures;
+  if (Not(CMPINT::LT) != CMPINT::NLT || Not(CMPINT::TRUE) != CMPINT::FALSE) ++failures;
+  {
+    NTT ntt(4, 0xffffffffffc0001ULL);
+    if (ntt.GetRootOfUnityPower(2) != 178930308976060547ULL) ++failures;
+    if (ntt.GetAVX512RootOfUnityPowers().size() < 4) ++failures;
+    NTT copy = ntt;  // copyable
+    NTT assigned;
+    assigned = NTT(8, 769);  // move-assignable (test/include/test/test-ntt-util.hpp:29)
+    if (assigned.GetDegree() != 8 || copy.GetModulus() != ntt.GetModulus()) ++failures;
+    CountingAllocator ca;
+    NTT with_alloc(8, 769, std::move(ca));
+    if (CountingAllocator::allocations == 0) ++failures;
+    std::allocator<int> sa;
+    (void)sa;
+  }
+  if (run) {
+    {
+      std::vector<uint64_t> op1{1, 2, 3, 4, 5, 6, 7, 8}, op2{1, 3, 5, 7, 2, 4, 6, 8};
+      EltwiseAddMod(op1.data(), op1.data(), op2.data(), op1.size(), 10);
+      Expect(op1, {2, 5, 8, 1, 7, 0, 3, 6}, "EltwiseAddMod vector-vector");
+    }
+    {
+      std::vector<uint64_t> op1{1, 2, 3, 4, 5, 6, 7, 8};
+      EltwiseAddMod(op1.data(), op1.data(), uint64_t(3), op1.size(), 10);
+      Expect(op1, {4, 5, 6, 7, 8, 9, 0, 1}, "EltwiseAddMod vector-scalar");
+    }
+    {
+      std::vector<uint64_t> op1{1, 2, 3, 4, 5, 6, 7, 8};
+      EltwiseCmpAdd(op1.data(), op1.data(), op1.size(), CMPINT::NLE, 3, 5);
+      Expect(op1, {1, 2, 3, 9, 10, 11, 12, 13}, "EltwiseCmpAdd");
+    }
+    {
+      std::vector<uint64_t> op1{1, 2, 3, 4, 5, 6, 7};
+      EltwiseCmpSubMod(op1.data(), op1.data(), op1.size(), 10, CMPINT::NLE, 4, 5);
+      Expect(op1, {1, 2, 3, 4, 0, 1, 2}, "EltwiseCmpSubMod");
+    }
+    {
+      std::vector<uint64_t> arg1{1, 2, 3, 4, 5, 6, 7, 8, 9};
+      EltwiseFMAMod(arg1.data(), arg1.data(), 1, nullptr, arg1.size(), 769, 1);
+      Expect(arg1, {1, 2, 3, 4, 5, 6, 7, 8, 9}, "EltwiseFMAMod");
+    }
+    {
+      std::vector<uint64_t> op1{2, 4, 3, 2}, op2{2, 1, 2, 0};
+      EltwiseMultMod(op1.data(), op1.data(), op2.data(), op1.size(), 769, 1);
+      Expect(op1, {4, 4, 6, 0}, "EltwiseMultMod");
+    }
+    {
+      std::vector<uint64_t> arg{1, 2, 3, 4, 5, 6, 7, 8};
+      const auto want = arg;
+      NTT ntt(8, 769);
+      ntt.ComputeForward(arg.data(), arg.data(), 1, 1);
+      ntt.ComputeInverse(arg.data(), arg.data(), 1, 1);
+      Expect(arg, want, "NTT round trip");
+    }
+    {
+      std::vector<uint64_t> arg{1, 2, 3, 4, 5, 6, 7, 8}, result(8, 0);
+      EltwiseReduceMod(result.data(), arg.data(), arg.size(), 5, 2, 1);
+      Expect(result, {1, 2, 3, 4, 0, 1, 2, 3}, "EltwiseReduceMod");
+    }
+    {
+      // the 32-point known answer of test/test-ntt.cpp:391-403
+      std::vector<uint64_t> in{401, 203, 221, 352, 487, 151, 405, 356, 343, 424, 635, 757, 457, 280, 624, 353,
+                               496, 353, 624, 280, 457, 757, 635, 424, 343, 356, 405, 151, 487, 352, 221, 203};
+      std::vector<uint64_t> want(32), out(32);
+      for (int i = 0; i < 32; ++i) want[i] = i + 1;
+      NTT ntt(32, 769);
+      ntt.ComputeForward(out.data(), in.data(), 1, 1);
+      Expect(out, want, "NTT N=32 known answer");
+    }
+    bool threw = false;
+    try {
+      std::vector<uint64_t> a{1, 2};
+      EltwiseMultMod(a.data(), a.data(), a.data(), 2, 769, 3);  // bad input_mod_factor
+    } catch (const std::runtime_error&) {
+      threw = true;
+    }
+    if (!threw) ++failures;
+  }
+  std::printf(failures ? "FAILED (%d)\n" : "ok%.0d\n", failures);
+  return failures ? 1 : 0;
+}

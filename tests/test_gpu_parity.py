@@ -352,3 +352,22 @@ def test_kernels_really_launch(hb):
     hb.NTT(1024, q).ComputeForward(d, d, 1, 1)
     torch.cuda.synchronize()
     assert hb.launch_count() > before
+
+
+def test_cpp_drop_in_caller_runs(hb, tmp_path):
+    """The reference-style C++ caller (tests/cpp/example_caller.cpp: the scenarios of
+    example/example.cpp plus the N=32 known answer) through include/hexl/hexl.hpp,
+    with plain host vectors exactly as an unmodified SEAL/OpenFHE-style caller passes."""
+    import os
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("g++ not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "example_caller"
+    libdir = os.path.dirname(hb.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "cpp", "example_caller.cpp"), "-o", str(exe),
+                    "-L", libdir, "-lhexl_b200", f"-Wl,-rpath,{libdir}"], check=True)
+    res = subprocess.run([str(exe), "run"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
