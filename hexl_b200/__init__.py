@@ -23,7 +23,7 @@ from enum import IntEnum
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhexl_b200.so")
+LIB_PATH = os.environ.get("HEXL_B200_LIB") or os.path.join(_HERE, "lib", "libhexl_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

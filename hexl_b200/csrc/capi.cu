@@ -351,6 +351,7 @@ int device_tables(hexl_b200_ntt* h, int dev, NttDeviceTables* out) {
   out->n = h->n;
   out->log_n = h->log_n;
   out->q = h->q;
+  out->mu = nt::multiply_factor(1, 64, h->q);
   out->inv_n = h->inv_n;
   out->inv_n_w = h->inv_n_w;
   return 0;

@@ -43,6 +43,7 @@ struct NttDeviceTables {
   u64 n;
   int log_n;
   u64 q;
+  u64 mu;           // floor(2^64 / q)
   Twiddle inv_n;    // N^-1 and its Shoup factor
   Twiddle inv_n_w;  // N^-1 * inv[1] and its Shoup factor
 };

@@ -33,32 +33,44 @@
 namespace hexl_b200 {
 namespace {
 
-// ----------------------------------------------------------------- butterflies
+// ----------------------------------------------------------------- arithmetic
+// B200 has no 64-bit integer multiplier; a 64x64 product is built from 32-bit
+// IMADs (FMA pipe, full rate) while 64-bit adds/compares/selects cost two
+// half-rate ALU-pipe instructions each.  Everything below is therefore written
+// as multiply-add chains on 32-bit limbs, with as few compares as possible.
+//
+// Two arithmetic modes, chosen per modulus at launch time:
+//
+//  GENERIC (any q < 2^62): Harvey's lazy butterflies exactly as the reference
+//    states them (ntt-default.hpp:28-42,112-125): forward values stay in [0,4q),
+//    inverse values in [0,2q), one conditional subtraction per butterfly.
+//
+//  FAST (q < 2^56): the 2^64/q >= 256 of headroom replaces the per-butterfly
+//    conditional subtractions.  The Shoup quotient is estimated from three 32x32
+//    partial products (no lo*lo term, no carry between the middle terms: low by
+//    at most 2), so a twiddle product lands in [0,4q).  Forward: X' = X + T,
+//    Y' = X + 4q - T, ranges grow by 4q per stage (<= (4 + 4*20) q = 84q < 2^63)
+//    and one Barrett reduction per coefficient at the very end restores [0,q).
+//    Inverse: sums are left unreduced inside a register pass; a pass that starts
+//    with all values < 8q ends with slot bounds 4*2^(K-1-h) q (h = highest set
+//    register bit) or 8*2^K q (all-sum slots), and only slots above 8q are
+//    Barrett-reduced at the pass boundary (4 of 16 for a 4-stage pass).  The
+//    largest transient is 2 * 8*2^4 * q = 256q < 2^64 for q < 2^56.
+//  Both modes produce the same canonical values; lazy outputs (out_mf 4 / 2)
+//  are congruent and inside the advertised range.
+enum : int { kGeneric = 0, kFast = 1 };
+constexpr u64 kFastModulusLimit = 1ull << 56;
+constexpr int kFastProd = 4;   // FAST: a twiddle product is < 4q
+constexpr int kFastBound = 8;  // FAST inverse: every value is < 8q at a pass boundary
 
-// Harvey forward butterfly, X,Y in [0,4q) -> [0,4q)   (ntt-default.hpp:28-42)
-__device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, const Twiddle w, u64 q, u64 two_q) {
-  u64 tx = csub(X, two_q);
-  u64 T = shoup_lazy(Y, w.w, w.wp, q);
-  X = tx + T;
-  Y = tx + two_q - T;
-}
+struct Mod {
+  u64 q, two_q, four_q, mu;  // mu = floor(2^64 / q)
+  unsigned n0, n1;           // low / high word of 2^64 - q
+};
 
-// Harvey inverse butterfly, X,Y in [0,2q) -> [0,2q)   (ntt-default.hpp:112-125)
-__device__ __forceinline__ void inv_bfly(u64& X, u64& Y, const Twiddle w, u64 q, u64 two_q) {
-  u64 s = X + Y;
-  u64 d = X + two_q - Y;
-  X = csub(s, two_q);
-  Y = shoup_lazy(d, w.w, w.wp, q);
-}
-
-// Last inverse stage with N^-1 folded in (ntt-radix-2.cpp:484-509)
-__device__ __forceinline__ void inv_bfly_last(u64& X, u64& Y, const Twiddle inv_n,
-                                              const Twiddle inv_n_w, u64 q, u64 two_q) {
-  u64 s = csub(X + Y, two_q);
-  u64 d = X + two_q - Y;
-  X = shoup_lazy(s, inv_n.w, inv_n.wp, q);
-  Y = shoup_lazy(d, inv_n_w.w, inv_n_w.wp, q);
-}
+__device__ __forceinline__ unsigned lo32(u64 x) { return (unsigned)x; }
+__device__ __forceinline__ unsigned hi32(u64 x) { return (unsigned)(x >> 32); }
+__device__ __forceinline__ u64 join(unsigned lo, unsigned hi) { return ((u64)hi << 32) | lo; }
 
 __device__ __forceinline__ Twiddle ld_tw(const Twiddle* p) {
   const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
@@ -68,13 +80,120 @@ __device__ __forceinline__ Twiddle ld_tw(const Twiddle* p) {
   return t;
 }
 
-// forward output range: [0,4q) -> [0,q) when out_mf == 1  (ntt-radix-2.cpp:254-260)
-__device__ __forceinline__ u64 fwd_out(u64 v, u64 q, u64 two_q, int out_mf) {
-  return out_mf == 1 ? csub(csub(v, two_q), q) : v;
+// floor(a*b / 2^64) - {0,1,2}: a1*b1 + hi32(a1*b0) + hi32(a0*b1)
+__device__ __forceinline__ u64 mulhi_approx(u64 a, u64 b) {
+  const unsigned a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+  return (u64)a1 * b1 + (u64)__umulhi(a1, b0) + (u64)__umulhi(a0, b1);
 }
-// inverse output range: [0,2q) -> [0,q) when out_mf == 1  (ntt-radix-2.cpp:511-518)
-__device__ __forceinline__ u64 inv_out(u64 v, u64 q, int out_mf) {
-  return out_mf == 1 ? csub(v, q) : v;
+
+// low 64 bits of c + x*w + Q*(2^64 - q) as one chain of 2 wide and 4 narrow IMADs
+__device__ __forceinline__ u64 mad_chain(u64 x, u64 w, u64 Q, const Mod& m) {
+  const unsigned x0 = lo32(x), x1 = hi32(x), w0 = lo32(w), w1 = hi32(w);
+  const unsigned q0 = lo32(Q), q1 = hi32(Q);
+  u64 t = (u64)x0 * w0;
+  t = (u64)q0 * m.n0 + t;
+  unsigned h = hi32(t);
+  h = x0 * w1 + h;
+  h = x1 * w0 + h;
+  h = q0 * m.n1 + h;
+  h = q1 * m.n0 + h;
+  return join(lo32(t), h);
+}
+
+// x*w mod q, lazily: exact quotient -> [0,2q); approximate quotient -> [0,4q)
+template <int MODE>
+__device__ __forceinline__ u64 mul_tw(u64 x, const Twiddle w, const Mod& m) {
+  const u64 Q = MODE == kFast ? mulhi_approx(x, w.wp) : mulhi(x, w.wp);
+  return mad_chain(x, w.w, Q, m);
+}
+__device__ __forceinline__ u64 mul_tw_exact(u64 x, const Twiddle w, const Mod& m) {
+  return mad_chain(x, w.w, mulhi(x, w.wp), m);
+}
+
+// any 64-bit value -> [0,2q):  x - floor(x*mu/2^64)*q
+__device__ __forceinline__ u64 barrett_lazy(u64 x, const Mod& m) {
+  const u64 Q = mulhi(x, m.mu);
+  const unsigned q0 = lo32(Q), q1 = hi32(Q);
+  u64 t = (u64)q0 * m.n0 + x;
+  unsigned h = hi32(t);
+  h = q0 * m.n1 + h;
+  h = q1 * m.n0 + h;
+  return join(lo32(t), h);
+}
+
+// ----------------------------------------------------------------- butterflies
+template <int MODE>
+__device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, const Twiddle w, const Mod& m) {
+  if (MODE == kFast) {
+    const u64 T = mul_tw<kFast>(Y, w, m);  // [0,4q)
+    Y = X + m.four_q - T;
+    X = X + T;
+  } else {
+    const u64 tx = csub(X, m.two_q);
+    const u64 T = mul_tw<kGeneric>(Y, w, m);  // [0,2q)
+    X = tx + T;
+    Y = tx + m.two_q - T;
+  }
+}
+
+// cq: a multiple of q at least as large as any Y of this stage (FAST only)
+template <int MODE>
+__device__ __forceinline__ void inv_bfly(u64& X, u64& Y, const Twiddle w, const Mod& m, u64 cq) {
+  if (MODE == kFast) {
+    const u64 d = X + cq - Y;
+    X = X + Y;
+    Y = mul_tw<kFast>(d, w, m);  // [0,4q)
+  } else {
+    const u64 s = X + Y;
+    const u64 d = X + m.two_q - Y;
+    X = csub(s, m.two_q);
+    Y = mul_tw<kGeneric>(d, w, m);
+  }
+}
+
+// Root stage of the inverse with N^-1 folded in (ntt-radix-2.cpp:484-509).  The
+// Shoup multiply accepts any 64-bit input, so the sum needs no reduction first.
+__device__ __forceinline__ void inv_bfly_last(u64& X, u64& Y, const Twiddle inv_n, const Twiddle inv_n_w,
+                                              const Mod& m, u64 cq) {
+  const u64 s = X + Y;
+  const u64 d = X + cq - Y;
+  X = mul_tw_exact(s, inv_n, m);    // [0,2q)
+  Y = mul_tw_exact(d, inv_n_w, m);  // [0,2q)
+}
+
+// forward output: GENERIC [0,4q) / FAST anything  ->  [0,q) (out_mf 1) or < 4q (out_mf 4)
+template <int MODE>
+__device__ __forceinline__ u64 fwd_out(u64 v, const Mod& m, int out_mf) {
+  if (MODE == kFast) {
+    v = barrett_lazy(v, m);  // [0,2q), fine for out_mf == 4 as well
+    return out_mf == 1 ? csub(v, m.q) : v;
+  }
+  return out_mf == 1 ? csub(csub(v, m.two_q), m.q) : v;
+}
+// inverse output after the folded root stage: [0,2q) -> [0,q) when out_mf == 1
+__device__ __forceinline__ u64 inv_out(u64 v, const Mod& m, int out_mf) {
+  return out_mf == 1 ? csub(v, m.q) : v;
+}
+
+// FAST inverse bookkeeping.  After K unreduced GS stages on register bits 0..K-1
+// of values that all started below kFastBound*q, the slot whose low K bits are
+// `low` is bounded by (in units of q):
+__host__ __device__ constexpr int inv_slot_bound(int K, int low) {
+  if (low == 0) return kFastBound << K;
+  int h = 0;
+  for (int b = 0; b < K; ++b)
+    if (low & (1 << b)) h = b;
+  return kFastProd << (K - 1 - h);
+}
+// the largest Y entering GS stage s of such a pass (what cq must cover)
+__host__ __device__ constexpr int inv_stage_cover(int s) { return kFastBound << s; }
+
+template <int K, int NSLOTS, int E = 0>
+__device__ __forceinline__ void inv_pass_fixup(u64* v, const Mod& m) {
+  if constexpr (E < NSLOTS) {
+    if constexpr (inv_slot_bound(K, E & ((1 << K) - 1)) > kFastBound) v[E] = barrett_lazy(v[E], m);
+    inv_pass_fixup<K, NSLOTS, E + 1>(v, m);
+  }
 }
 
 // --------------------------------------------------------------- row kernel
@@ -92,36 +211,41 @@ __device__ __forceinline__ unsigned reg_index(unsigned u, int e) {
 }
 
 // Butterfly stages on row-local index bits HB..LOB (all inside [LB, LB+3]).
-// FWD: bits descend (CT).  INV: bits ascend (GS).
-template <int LOGC, int LB, int HB, int LOB, bool FWD>
+// FWD: bits descend (CT).  INV: bits ascend (GS), LOB == LB.
+template <int MODE, int LOGC, int LB, int HB, int LOB, bool FWD>
 __device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
-                                           const Twiddle* __restrict__ tw, u64 q, u64 two_q,
-                                           bool fold, Twiddle inv_n, Twiddle inv_n_w) {
+                                           const Twiddle* __restrict__ tw, const Mod& m, bool fold,
+                                           Twiddle inv_n, Twiddle inv_n_w) {
 #pragma unroll
   for (int step = 0; step <= HB - LOB; ++step) {
     const int beta = FWD ? HB - step : LOB + step;  // index bit of this stage
     const int eb = beta - LB;                       // register bit
     const int sp = LOGC - 1 - beta;                 // stage number inside the row
     const u64 node0 = (base << sp) + ((u64)(u >> LB) << (LB + 3 - beta));
+    // FAST inverse: multiple of q covering every Y of this stage (GENERIC: 2q)
+    const u64 cq = (!FWD && MODE == kFast) ? (u64)inv_stage_cover(step) * m.q : m.two_q;
     if (!FWD && sp == 0 && fold) {
       // root stage of the whole transform: one group, N^-1 folded in
 #pragma unroll
-      for (int l = 0; l < (1 << eb); ++l) inv_bfly_last(v[l], v[l | (1 << eb)], inv_n, inv_n_w, q, two_q);
+      for (int l = 0; l < (1 << eb); ++l) inv_bfly_last(v[l], v[l | (1 << eb)], inv_n, inv_n_w, m, cq);
     } else {
+      Twiddle w[8];
+#pragma unroll
+      for (int g = 0; g < (8 >> eb); ++g) w[g] = ld_tw(tw + node0 + g);
 #pragma unroll
       for (int g = 0; g < (8 >> eb); ++g) {
-        const Twiddle w = ld_tw(tw + node0 + g);
 #pragma unroll
         for (int l = 0; l < (1 << eb); ++l) {
           const int e = (g << (eb + 1)) | l;
           if (FWD)
-            fwd_bfly(v[e], v[e | (1 << eb)], w, q, two_q);
+            fwd_bfly<MODE>(v[e], v[e | (1 << eb)], w[g], m);
           else
-            inv_bfly(v[e], v[e | (1 << eb)], w, q, two_q);
+            inv_bfly<MODE>(v[e], v[e | (1 << eb)], w[g], m, cq);
         }
       }
     }
   }
+  if (!FWD && MODE == kFast && !(fold && LOGC - 1 - HB == 0)) inv_pass_fixup<HB - LOB + 1, 16>(v, m);
 }
 
 template <int LB_FROM, int LB_TO>
@@ -135,35 +259,39 @@ __device__ __forceinline__ void smem_exchange(u64 (&v)[16], u64* srow, unsigned 
 }
 
 // Forward passes after pass 0: register bits move down by 4 per pass, clamped at 0.
-template <int LOGC, int PASS>
+template <int MODE, int LOGC, int PASS>
 __device__ __forceinline__ void fwd_passes(u64 (&v)[16], u64* srow, unsigned u, u64 base,
-                                           const Twiddle* tw, u64 q, u64 two_q) {
+                                           const Twiddle* tw, const Mod& m) {
   constexpr int PREV_LB = (LOGC - 4 * PASS) > 0 ? (LOGC - 4 * PASS) : 0;
   constexpr int HB = LOGC - 4 * PASS - 1;  // highest index bit not yet processed
   if constexpr (HB >= 0) {
     constexpr int LB = (HB - 3) > 0 ? (HB - 3) : 0;
     smem_exchange<PREV_LB, LB>(v, srow, u);
-    reg_stages<LOGC, LB, HB, LB, true>(v, u, base, tw, q, two_q, false, Twiddle{}, Twiddle{});
-    fwd_passes<LOGC, PASS + 1>(v, srow, u, base, tw, q, two_q);
+    reg_stages<MODE, LOGC, LB, HB, LB, true>(v, u, base, tw, m, false, Twiddle{}, Twiddle{});
+    fwd_passes<MODE, LOGC, PASS + 1>(v, srow, u, base, tw, m);
   }
 }
 
 // Inverse passes: mirror image.  PASS counts down; pass P-1 is done first.
-template <int LOGC, int PASS>
+template <int MODE, int LOGC, int PASS>
 __device__ __forceinline__ void inv_passes(u64 (&v)[16], u64* srow, unsigned u, u64 base,
-                                           const Twiddle* tw, u64 q, u64 two_q, bool fold,
-                                           Twiddle inv_n, Twiddle inv_n_w) {
+                                           const Twiddle* tw, const Mod& m, bool fold, Twiddle inv_n,
+                                           Twiddle inv_n_w) {
   // forward pass PASS handled bits HB..LB; the inverse handles the same bits ascending
   constexpr int HB = LOGC - 4 * PASS - 1;
   constexpr int LB = (HB - 3) > 0 ? (HB - 3) : 0;
-  reg_stages<LOGC, LB, HB, LB, false>(v, u, base, tw, q, two_q, fold, inv_n, inv_n_w);
+  reg_stages<MODE, LOGC, LB, HB, LB, false>(v, u, base, tw, m, fold, inv_n, inv_n_w);
   if constexpr (PASS > 0) {
     constexpr int NHB = LOGC - 4 * (PASS - 1) - 1;
     constexpr int NLB = (NHB - 3) > 0 ? (NHB - 3) : 0;
     smem_exchange<LB, NLB>(v, srow, u);
-    inv_passes<LOGC, PASS - 1>(v, srow, u, base, tw, q, two_q, fold, inv_n, inv_n_w);
+    inv_passes<MODE, LOGC, PASS - 1>(v, srow, u, base, tw, m, fold, inv_n, inv_n_w);
   }
 }
+
+#ifndef HEXL_B200_ROW_MIN_BLOCKS
+#define HEXL_B200_ROW_MIN_BLOCKS 2
+#endif
 
 template <int LOGC>
 struct RowCfg {
@@ -173,12 +301,13 @@ struct RowCfg {
   static constexpr int THREADS = T * ROWS;
   static constexpr int PASSES = (LOGC + 3) / 4;
   static constexpr size_t SMEM = (size_t)ROWS * C * sizeof(u64);
+  static constexpr int MIN_BLOCKS = THREADS <= 256 ? HEXL_B200_ROW_MIN_BLOCKS : 1;
 };
 
 // One CTA = ROWS rows of C contiguous coefficients.  rows_per_poly = N / C.
-template <int LOGC>
-__global__ void __launch_bounds__(RowCfg<LOGC>::THREADS)
-    ntt_row_fwd(u64* result, const u64* operand, const Twiddle* __restrict__ tw, u64 q,
+template <int MODE, int LOGC>
+__global__ void __launch_bounds__(RowCfg<LOGC>::THREADS, RowCfg<LOGC>::MIN_BLOCKS)
+    ntt_row_fwd(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m,
                 u64 total_rows, unsigned rows_per_poly, int out_mf) {
   using Cfg = RowCfg<LOGC>;
   extern __shared__ __align__(16) u64 smem[];
@@ -187,7 +316,6 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS)
   const bool active = row < total_rows;
   if (!active) row = total_rows - 1;  // keep barriers uniform; stores are masked
   const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
-  const u64 two_q = q << 1;
   const u64* in = operand + row * Cfg::C;
   u64* out = result + row * Cfg::C;
   u64* srow = smem + (size_t)row_local * Cfg::C;
@@ -196,9 +324,11 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS)
   constexpr int LB0 = LOGC - 4;  // pass 0: register bits are the top 4 index bits
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = __ldcs(in + reg_index<LB0>(u, e));
-  reg_stages<LOGC, LB0, LOGC - 1, LB0, true>(v, u, base, tw, q, two_q, false, Twiddle{}, Twiddle{});
-  fwd_passes<LOGC, 1>(v, srow, u, base, tw, q, two_q);
+  reg_stages<MODE, LOGC, LB0, LOGC - 1, LB0, true>(v, u, base, tw, m, false, Twiddle{}, Twiddle{});
+  fwd_passes<MODE, LOGC, 1>(v, srow, u, base, tw, m);
   // registers now hold 16 consecutive coefficients per thread (LB = 0)
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = fwd_out<MODE>(v[e], m, out_mf);
   if constexpr (LOGC > 4) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) srow[swz(reg_index<0>(u, e))] = v[e];
@@ -208,13 +338,13 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS)
   }
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) __stcs(out + reg_index<LB0>(u, e), fwd_out(v[e], q, two_q, out_mf));
+    for (int e = 0; e < 16; ++e) __stcs(out + reg_index<LB0>(u, e), v[e]);
   }
 }
 
-template <int LOGC>
-__global__ void __launch_bounds__(RowCfg<LOGC>::THREADS)
-    ntt_row_inv(u64* result, const u64* operand, const Twiddle* __restrict__ tw, u64 q,
+template <int MODE, int LOGC>
+__global__ void __launch_bounds__(RowCfg<LOGC>::THREADS, RowCfg<LOGC>::MIN_BLOCKS)
+    ntt_row_inv(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m,
                 u64 total_rows, unsigned rows_per_poly, int out_mf, int fold, Twiddle inv_n,
                 Twiddle inv_n_w) {
   using Cfg = RowCfg<LOGC>;
@@ -224,7 +354,6 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS)
   const bool active = row < total_rows;
   if (!active) row = total_rows - 1;
   const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
-  const u64 two_q = q << 1;
   const u64* in = operand + row * Cfg::C;
   u64* out = result + row * Cfg::C;
   u64* srow = smem + (size_t)row_local * Cfg::C;
@@ -242,13 +371,13 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS)
     for (int e = 0; e < 16; ++e) v[e] = srow[swz(reg_index<0>(u, e))];
     __syncthreads();
   }
-  inv_passes<LOGC, Cfg::PASSES - 1>(v, srow, u, base, tw, q, two_q, fold != 0, inv_n, inv_n_w);
+  inv_passes<MODE, LOGC, Cfg::PASSES - 1>(v, srow, u, base, tw, m, fold != 0, inv_n, inv_n_w);
   // last pass left the registers in the coalesced layout (LB = LOGC-4)
   if (active) {
     const bool final_out = fold != 0;  // only the kernel holding the root stage reduces
 #pragma unroll
     for (int e = 0; e < 16; ++e)
-      __stcs(out + reg_index<LB0>(u, e), final_out ? inv_out(v[e], q, out_mf) : v[e]);
+      __stcs(out + reg_index<LB0>(u, e), final_out ? inv_out(v[e], m, out_mf) : v[e]);
   }
 }
 
@@ -257,9 +386,9 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS)
 // (N/S) + block_index.  A thread owns column c of one sub-block: R coefficients
 // at stride S/R, and runs the sub-block's first log2(R) stages (forward) or last
 // log2(R) stages (inverse) on them in registers.
-template <int LOGR, bool FWD>
+template <int MODE, int LOGR, bool FWD>
 __global__ void __launch_bounds__(256)
-    ntt_col(u64* result, const u64* operand, const Twiddle* __restrict__ tw, u64 q, int log_n,
+    ntt_col(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m, int log_n,
             int log_s, u64 total_cols, int out_mf, int fold, Twiddle inv_n, Twiddle inv_n_w) {
   constexpr int R = 1 << LOGR;
   __shared__ Twiddle stw[R];
@@ -279,7 +408,7 @@ __global__ void __launch_bounds__(256)
   if (g >= total_cols) return;
   const u64 c = g & ((1ull << log_cols) - 1);
   const u64 off = (blk << log_s) + c;
-  const u64 two_q = q << 1;
+  const bool root = log_s == log_n;                  // this pass contains the root stage
   u64 v[R];
 #pragma unroll
   for (int e = 0; e < R; ++e) v[e] = __ldcs(operand + off + ((u64)e << log_cols));
@@ -287,9 +416,10 @@ __global__ void __launch_bounds__(256)
   for (int step = 0; step < LOGR; ++step) {
     const int s = FWD ? step : LOGR - 1 - step;      // stage inside the sub-block
     const int eb = LOGR - 1 - s;                     // register bit
-    if (!FWD && fold && s == 0 && log_s == log_n) {
+    const u64 cq = (!FWD && MODE == kFast) ? (u64)inv_stage_cover(step) * m.q : m.two_q;
+    if (!FWD && fold && s == 0 && root) {
 #pragma unroll
-      for (int l = 0; l < (1 << eb); ++l) inv_bfly_last(v[l], v[l | (1 << eb)], inv_n, inv_n_w, q, two_q);
+      for (int l = 0; l < (1 << eb); ++l) inv_bfly_last(v[l], v[l | (1 << eb)], inv_n, inv_n_w, m, cq);
     } else {
 #pragma unroll
       for (int gi = 0; gi < (1 << s); ++gi) {
@@ -298,24 +428,25 @@ __global__ void __launch_bounds__(256)
         for (int l = 0; l < (1 << eb); ++l) {
           const int e = (gi << (eb + 1)) | l;
           if (FWD)
-            fwd_bfly(v[e], v[e | (1 << eb)], w, q, two_q);
+            fwd_bfly<MODE>(v[e], v[e | (1 << eb)], w, m);
           else
-            inv_bfly(v[e], v[e | (1 << eb)], w, q, two_q);
+            inv_bfly<MODE>(v[e], v[e | (1 << eb)], w, m, cq);
         }
       }
     }
   }
-  const bool final_out = !FWD && fold && log_s == log_n;
+  const bool final_out = !FWD && fold && root;
+  if (!FWD && MODE == kFast && !final_out) inv_pass_fixup<LOGR, R>(v, m);
 #pragma unroll
   for (int e = 0; e < R; ++e)
-    __stcs(result + off + ((u64)e << log_cols), final_out ? inv_out(v[e], q, out_mf) : v[e]);
+    __stcs(result + off + ((u64)e << log_cols), final_out ? inv_out(v[e], m, out_mf) : v[e]);
 }
 
 // --------------------------------------------------------- tiny-N stage kernel
-// One radix-2 stage per launch on global memory; used for N < 16.
+// One radix-2 stage per launch on global memory; used for N < 16 (GENERIC mode).
 template <bool FWD>
 __global__ void ntt_stage_simple(u64* result, const u64* src, const Twiddle* __restrict__ tw,
-                                 u64 q, int log_n, int s /*stage: m = 2^s groups*/,
+                                 const Mod m, int log_n, int s /*stage: m = 2^s groups*/,
                                  u64 total_bflies, int out_mf, int last, Twiddle inv_n,
                                  Twiddle inv_n_w) {
   const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
@@ -325,20 +456,19 @@ __global__ void ntt_stage_simple(u64* result, const u64* src, const Twiddle* __r
   const u64 poly = g >> (log_n - 1), k = g & (half - 1);
   const u64 i = k >> log_t, jj = k & ((1ull << log_t) - 1);
   const u64 j = (poly << log_n) + (i << (log_t + 1)) + jj;
-  const u64 two_q = q << 1;
   u64 X = src[j], Y = src[j + (1ull << log_t)];
   if (FWD) {
-    fwd_bfly(X, Y, ld_tw(tw + (1ull << s) + i), q, two_q);
+    fwd_bfly<kGeneric>(X, Y, ld_tw(tw + (1ull << s) + i), m);
     if (last) {
-      X = fwd_out(X, q, two_q, out_mf);
-      Y = fwd_out(Y, q, two_q, out_mf);
+      X = fwd_out<kGeneric>(X, m, out_mf);
+      Y = fwd_out<kGeneric>(Y, m, out_mf);
     }
   } else if (last) {
-    inv_bfly_last(X, Y, inv_n, inv_n_w, q, two_q);
-    X = inv_out(X, q, out_mf);
-    Y = inv_out(Y, q, out_mf);
+    inv_bfly_last(X, Y, inv_n, inv_n_w, m, m.two_q);
+    X = inv_out(X, m, out_mf);
+    Y = inv_out(Y, m, out_mf);
   } else {
-    inv_bfly(X, Y, ld_tw(tw + (1ull << s) + i), q, two_q);
+    inv_bfly<kGeneric>(X, Y, ld_tw(tw + (1ull << s) + i), m, m.two_q);
   }
   result[j] = X;
   result[j + (1ull << log_t)] = Y;
@@ -354,7 +484,7 @@ int env_int(const char* name, int dflt) {
 // log2 of the row length used for a transform of size 2^log_n
 int pick_row_log(int log_n) {
   static const int max_row = [] {
-    int v = env_int("HEXL_B200_MAX_ROW_LOG", 14);
+    int v = env_int("HEXL_B200_MAX_ROW_LOG", 13);
     return v < 4 ? 4 : (v > 14 ? 14 : v);
   }();
   static const int split_row = [] {
@@ -365,40 +495,59 @@ int pick_row_log(int log_n) {
   return split_row;
 }
 
-template <int LOGC>
+int pick_mode(u64 q) {
+  static const bool force_generic = env_int("HEXL_B200_FORCE_GENERIC", 0) != 0;
+  return (!force_generic && q < kFastModulusLimit) ? kFast : kGeneric;
+}
+
+Mod make_mod(const NttDeviceTables& t) {
+  Mod m;
+  m.q = t.q;
+  m.two_q = t.q << 1;
+  m.four_q = t.q << 2;
+  m.mu = t.mu;
+  const u64 negq = 0 - t.q;
+  m.n0 = (unsigned)negq;
+  m.n1 = (unsigned)(negq >> 32);
+  return m;
+}
+
+template <int MODE, int LOGC>
 cudaError_t launch_row(bool fwd, const NttDeviceTables& t, u64* result, const u64* operand,
                        u64 batch, int out_mf, int fold, cudaStream_t stream) {
   using Cfg = RowCfg<LOGC>;
   const unsigned rows_per_poly = (unsigned)(t.n >> LOGC);
   const u64 total_rows = batch * rows_per_poly;
   const unsigned grid = (unsigned)((total_rows + Cfg::ROWS - 1) / Cfg::ROWS);
+  const Mod m = make_mod(t);
   if (fwd) {
     if (Cfg::SMEM > 48 * 1024) {  // per-device attribute: set on every launch (cheap)
-      cudaError_t e = cudaFuncSetAttribute(ntt_row_fwd<LOGC>,
+      cudaError_t e = cudaFuncSetAttribute(ntt_row_fwd<MODE, LOGC>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
       if (e != cudaSuccess) return e;
     }
-    ntt_row_fwd<LOGC><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, t.fwd, t.q,
-                                                                 total_rows, rows_per_poly, out_mf);
+    ntt_row_fwd<MODE, LOGC><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, t.fwd, m, total_rows,
+                                                                       rows_per_poly, out_mf);
   } else {
     if (Cfg::SMEM > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(ntt_row_inv<LOGC>,
+      cudaError_t e = cudaFuncSetAttribute(ntt_row_inv<MODE, LOGC>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
       if (e != cudaSuccess) return e;
     }
-    ntt_row_inv<LOGC><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(
-        result, operand, t.inv, t.q, total_rows, rows_per_poly, out_mf, fold, t.inv_n, t.inv_n_w);
+    ntt_row_inv<MODE, LOGC><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(
+        result, operand, t.inv, m, total_rows, rows_per_poly, out_mf, fold, t.inv_n, t.inv_n_w);
   }
   count_launch();
   return cudaGetLastError();
 }
 
+template <int MODE>
 cudaError_t launch_row_dyn(int log_c, bool fwd, const NttDeviceTables& t, u64* result,
                            const u64* operand, u64 batch, int out_mf, int fold,
                            cudaStream_t stream) {
   switch (log_c) {
 #define ROW_CASE(L) \
-  case L: return launch_row<L>(fwd, t, result, operand, batch, out_mf, fold, stream);
+  case L: return launch_row<MODE, L>(fwd, t, result, operand, batch, out_mf, fold, stream);
     ROW_CASE(4) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7) ROW_CASE(8) ROW_CASE(9) ROW_CASE(10)
     ROW_CASE(11) ROW_CASE(12) ROW_CASE(13) ROW_CASE(14)
 #undef ROW_CASE
@@ -406,32 +555,34 @@ cudaError_t launch_row_dyn(int log_c, bool fwd, const NttDeviceTables& t, u64* r
   return cudaErrorInvalidValue;
 }
 
-template <int LOGR>
+template <int MODE, int LOGR>
 cudaError_t launch_col(bool fwd, const NttDeviceTables& t, u64* result, const u64* operand,
                        u64 batch, int log_s, int out_mf, int fold, cudaStream_t stream) {
   const u64 total_cols = (batch << t.log_n) >> LOGR;
   const u64 cols_per_block = 1ull << (log_s - LOGR);
   const unsigned threads = (unsigned)(cols_per_block < 256 ? cols_per_block : 256);
   const unsigned grid = (unsigned)((total_cols + threads - 1) / threads);
+  const Mod m = make_mod(t);
   if (fwd)
-    ntt_col<LOGR, true><<<grid, threads, 0, stream>>>(result, operand, t.fwd, t.q, t.log_n, log_s,
-                                                      total_cols, out_mf, fold, t.inv_n, t.inv_n_w);
+    ntt_col<MODE, LOGR, true><<<grid, threads, 0, stream>>>(result, operand, t.fwd, m, t.log_n, log_s,
+                                                            total_cols, out_mf, fold, t.inv_n, t.inv_n_w);
   else
-    ntt_col<LOGR, false><<<grid, threads, 0, stream>>>(result, operand, t.inv, t.q, t.log_n, log_s,
-                                                       total_cols, out_mf, fold, t.inv_n, t.inv_n_w);
+    ntt_col<MODE, LOGR, false><<<grid, threads, 0, stream>>>(result, operand, t.inv, m, t.log_n, log_s,
+                                                             total_cols, out_mf, fold, t.inv_n, t.inv_n_w);
   count_launch();
   return cudaGetLastError();
 }
 
+template <int MODE>
 cudaError_t launch_col_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64* result,
                            const u64* operand, u64 batch, int log_s, int out_mf, int fold,
                            cudaStream_t stream) {
   switch (log_r) {
-    case 1: return launch_col<1>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
-    case 2: return launch_col<2>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
-    case 3: return launch_col<3>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
-    case 4: return launch_col<4>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
-    case 5: return launch_col<5>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
+    case 1: return launch_col<MODE, 1>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
+    case 2: return launch_col<MODE, 2>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
+    case 3: return launch_col<MODE, 3>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
+    case 4: return launch_col<MODE, 4>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
+    case 5: return launch_col<MODE, 5>(fwd, t, result, operand, batch, log_s, out_mf, fold, stream);
   }
   return cudaErrorInvalidValue;
 }
@@ -454,19 +605,56 @@ cudaError_t simple_transform(bool fwd, const NttDeviceTables& t, u64* result, co
   const u64 total = batch << (t.log_n - 1);
   const unsigned threads = 128, grid = (unsigned)((total + threads - 1) / threads);
   const u64* src = operand;
+  const Mod m = make_mod(t);
   for (int k = 0; k < t.log_n; ++k) {
     const int s = fwd ? k : t.log_n - 1 - k;
     const int last = k == t.log_n - 1;
     if (fwd)
-      ntt_stage_simple<true><<<grid, threads, 0, stream>>>(result, src, t.fwd, t.q, t.log_n, s, total,
+      ntt_stage_simple<true><<<grid, threads, 0, stream>>>(result, src, t.fwd, m, t.log_n, s, total,
                                                            out_mf, last, t.inv_n, t.inv_n_w);
     else
-      ntt_stage_simple<false><<<grid, threads, 0, stream>>>(result, src, t.inv, t.q, t.log_n, s, total,
+      ntt_stage_simple<false><<<grid, threads, 0, stream>>>(result, src, t.inv, m, t.log_n, s, total,
                                                             out_mf, last, t.inv_n, t.inv_n_w);
     count_launch();
     src = result;
   }
   return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
+                         u64 batch, cudaStream_t stream) {
+  const int log_c = pick_row_log(t.log_n);
+  int radices[8];
+  const int ncol = plan_col_passes(t.log_n - log_c, radices);
+  const u64* src = operand;
+  int log_s = t.log_n;
+  for (int p = 0; p < ncol; ++p) {
+    cudaError_t e = launch_col_dyn<MODE>(radices[p], true, t, result, src, batch, log_s, out_mf, 0, stream);
+    if (e != cudaSuccess) return e;
+    log_s -= radices[p];
+    src = result;
+  }
+  return launch_row_dyn<MODE>(log_c, true, t, result, src, batch, out_mf, 0, stream);
+}
+
+template <int MODE>
+cudaError_t inverse_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
+                         u64 batch, cudaStream_t stream) {
+  const int log_c = pick_row_log(t.log_n);
+  int radices[8];
+  const int ncol = plan_col_passes(t.log_n - log_c, radices);
+  // the kernel that contains the root stage folds N^-1 and applies out_mf
+  cudaError_t e = launch_row_dyn<MODE>(log_c, false, t, result, operand, batch, out_mf, ncol == 0, stream);
+  if (e != cudaSuccess) return e;
+  // column passes in reverse: innermost (smallest sub-blocks) first
+  int log_s = log_c;
+  for (int p = ncol - 1; p >= 0; --p) {
+    log_s += radices[p];
+    e = launch_col_dyn<MODE>(radices[p], false, t, result, result, batch, log_s, out_mf, p == 0, stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace
@@ -475,38 +663,16 @@ cudaError_t launch_ntt_forward(const NttDeviceTables& t, u64* result, const u64*
                                int /*in_mf*/, int out_mf, u64 batch, cudaStream_t stream) {
   if (batch == 0) return cudaSuccess;
   if (t.log_n < 4) return simple_transform(true, t, result, operand, out_mf, batch, stream);
-  const int log_c = pick_row_log(t.log_n);
-  int radices[8];
-  const int ncol = plan_col_passes(t.log_n - log_c, radices);
-  const u64* src = operand;
-  int log_s = t.log_n;
-  for (int p = 0; p < ncol; ++p) {
-    cudaError_t e = launch_col_dyn(radices[p], true, t, result, src, batch, log_s, out_mf, 0, stream);
-    if (e != cudaSuccess) return e;
-    log_s -= radices[p];
-    src = result;
-  }
-  return launch_row_dyn(log_c, true, t, result, src, batch, out_mf, 0, stream);
+  return pick_mode(t.q) == kFast ? forward_impl<kFast>(t, result, operand, out_mf, batch, stream)
+                                 : forward_impl<kGeneric>(t, result, operand, out_mf, batch, stream);
 }
 
 cudaError_t launch_ntt_inverse(const NttDeviceTables& t, u64* result, const u64* operand,
                                int /*in_mf*/, int out_mf, u64 batch, cudaStream_t stream) {
   if (batch == 0) return cudaSuccess;
   if (t.log_n < 4) return simple_transform(false, t, result, operand, out_mf, batch, stream);
-  const int log_c = pick_row_log(t.log_n);
-  int radices[8];
-  const int ncol = plan_col_passes(t.log_n - log_c, radices);
-  // the kernel that contains the root stage folds N^-1 and applies out_mf
-  cudaError_t e = launch_row_dyn(log_c, false, t, result, operand, batch, out_mf, ncol == 0, stream);
-  if (e != cudaSuccess) return e;
-  // column passes in reverse: innermost (smallest sub-blocks) first
-  int log_s = log_c;
-  for (int p = ncol - 1; p >= 0; --p) {
-    log_s += radices[p];
-    e = launch_col_dyn(radices[p], false, t, result, result, batch, log_s, out_mf, p == 0, stream);
-    if (e != cudaSuccess) return e;
-  }
-  return cudaSuccess;
+  return pick_mode(t.q) == kFast ? inverse_impl<kFast>(t, result, operand, out_mf, batch, stream)
+                                 : inverse_impl<kGeneric>(t, result, operand, out_mf, batch, stream);
 }
 
 }  // namespace hexl_b200

@@ -106,21 +106,29 @@ def test_ntt_matches_oracle(hb, checker, logn, bits):
 
 
 def test_ntt_extreme_inputs(hb, checker):
-    """all-zero, all q-1, and lazy inputs at the top of their range (4q-1 / 2q-1),
-    at the largest supported modulus size (q just below 2^62)."""
-    for logn in (4, 10, 12, 15):
-        n = 1 << logn
-        q = hb.GeneratePrimes(1, 61, False, n)[0]  # largest primes below 2^62
-        assert q < (1 << 62)
-        t = hb.NTT(n, q)
-        for fill, in_mf in [(0, 1), (q - 1, 1), (4 * q - 1, 4), (2 * q - 1, 2)]:
-            x = np.full(n, fill, dtype=np.uint64)
-            o = dev(np.zeros_like(x))
-            t.ComputeForward(o, dev(x), in_mf, 1)
-            assert (host(o) == checker.ntt_forward(x, n, q, in_mf, 1)).all(), (logn, fill)
-            if in_mf <= 2:
-                t.ComputeInverse(o, dev(x), in_mf, 1)
-                assert (host(o) == checker.ntt_inverse(x, n, q, in_mf, 1)).all(), (logn, fill)
+    """all-zero, all q-1, and lazy inputs at the top of their range (4q-1 / 2q-1), at the
+    largest modulus of each arithmetic mode: q just below 2^62 (GENERIC butterflies) and
+    q just below 2^56 (FAST butterflies, where the lazy ranges come closest to 2^64),
+    including N = 2^17 whose column pass runs 5 unreduced stages."""
+    for bits in (61, 55):
+        for logn in (4, 10, 12, 15, 17):
+            n = 1 << logn
+            q = hb.GeneratePrimes(1, bits, False, n)[0]  # largest primes below 2^(bits+1)
+            assert q < (1 << (bits + 1)) and q > (1 << (bits + 1)) - (1 << 40)
+            t = hb.NTT(n, q)
+            for fill, in_mf in [(0, 1), (q - 1, 1), (4 * q - 1, 4), (2 * q - 1, 2)]:
+                x = np.full(n, fill, dtype=np.uint64)
+                x[1::3] = 0  # mix extremes so sums and differences both hit their bounds
+                o = dev(np.zeros_like(x))
+                t.ComputeForward(o, dev(x), in_mf, 1)
+                assert (host(o) == checker.ntt_forward(x, n, q, in_mf, 1)).all(), (bits, logn, fill)
+                if in_mf <= 2:
+                    t.ComputeInverse(o, dev(x), in_mf, 1)
+                    assert (host(o) == checker.ntt_inverse(x, n, q, in_mf, 1)).all(), (bits, logn, fill)
+                    t.ComputeInverse(o, dev(x), in_mf, 2)
+                    got = host(o)
+                    assert (got % np.uint64(q) == checker.ntt_inverse(x, n, q, in_mf, 1)).all()
+                    assert (got < np.uint64(2 * q)).all()
 
 
 def test_ntt_user_root(hb, checker):

@@ -1,0 +1,158 @@
+// Micro-benchmark: register-resident radix-16 butterfly networks, no memory
+// traffic in the loop.  Finds the issue-bound ceiling of each arithmetic
+// formulation so kernel changes can be judged against it.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tools/bin/bfly_bench tools/bfly_bench.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <stdint.h>
+typedef uint64_t u64;
+struct Tw { u64 w, wp; };
+struct Mod { u64 q, two_q, four_q, mu; unsigned n0, n1; };
+__device__ __forceinline__ unsigned lo32(u64 x) { return (unsigned)x; }
+__device__ __forceinline__ unsigned hi32(u64 x) { return (unsigned)(x >> 32); }
+__device__ __forceinline__ u64 join(unsigned lo, unsigned hi) { return ((u64)hi << 32) | lo; }
+__device__ __forceinline__ u64 csub(u64 x, u64 b) { u64 d = x - b; return x >= b ? d : x; }
+
+// ---- variant 0: GENERIC (Harvey) as first written
+__device__ __forceinline__ void bf0(u64& X, u64& Y, Tw w, const Mod& m) {
+  u64 tx = csub(X, m.two_q);
+  u64 Q = __umul64hi(Y, w.wp);
+  u64 T = Y * w.w - Q * m.q;
+  X = tx + T; Y = tx + m.two_q - T;
+}
+// ---- variant 1: FAST as in the library now
+__device__ __forceinline__ u64 mulhi_approx(u64 a, u64 b) {
+  const unsigned a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
+  return (u64)a1 * b1 + (u64)__umulhi(a1, b0) + (u64)__umulhi(a0, b1);
+}
+__device__ __forceinline__ u64 mad_chain(u64 x, u64 w, u64 Q, const Mod& m) {
+  const unsigned x0 = lo32(x), x1 = hi32(x), w0 = lo32(w), w1 = hi32(w), q0 = lo32(Q), q1 = hi32(Q);
+  u64 t = (u64)x0 * w0; t = (u64)q0 * m.n0 + t;
+  unsigned h = hi32(t);
+  h = x0 * w1 + h; h = x1 * w0 + h; h = q0 * m.n1 + h; h = q1 * m.n0 + h;
+  return join(lo32(t), h);
+}
+__device__ __forceinline__ void bf1(u64& X, u64& Y, Tw w, const Mod& m) {
+  u64 T = mad_chain(Y, w.w, mulhi_approx(Y, w.wp), m);
+  Y = X + m.four_q - T; X = X + T;
+}
+// ---- variant 2: FAST, PTX-pinned instruction selection
+__device__ __forceinline__ u64 madwide(unsigned a, unsigned b, u64 c) {
+  u64 r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r;
+}
+__device__ __forceinline__ u64 mulwide(unsigned a, unsigned b) {
+  u64 r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ unsigned madlo(unsigned a, unsigned b, unsigned c) {
+  unsigned r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r;
+}
+__device__ __forceinline__ void bf2(u64& X, u64& Y, Tw w, const Mod& m) {
+  unsigned y0, y1, p0, p1, w0, w1;
+  asm("mov.b64 {%0,%1}, %2;" : "=r"(y0), "=r"(y1) : "l"(Y));
+  asm("mov.b64 {%0,%1}, %2;" : "=r"(p0), "=r"(p1) : "l"(w.wp));
+  asm("mov.b64 {%0,%1}, %2;" : "=r"(w0), "=r"(w1) : "l"(w.w));
+  // Q ~ y1*p1 + hi(y1*p0) + hi(y0*p1), all as wide mads (FMA pipe only)
+  u64 Q = mulwide(y1, p1);
+  Q = madwide(__umulhi(y1, p0), 1u, Q);
+  Q = madwide(__umulhi(y0, p1), 1u, Q);
+  unsigned q0, q1;
+  asm("mov.b64 {%0,%1}, %2;" : "=r"(q0), "=r"(q1) : "l"(Q));
+  u64 t = mulwide(y0, w0);
+  t = madwide(q0, m.n0, t);
+  unsigned tl, th;
+  asm("mov.b64 {%0,%1}, %2;" : "=r"(tl), "=r"(th) : "l"(t));
+  th = madlo(y0, w1, th); th = madlo(y1, w0, th); th = madlo(q0, m.n1, th); th = madlo(q1, m.n0, th);
+  u64 T; asm("mov.b64 %0, {%1,%2};" : "=l"(T) : "r"(tl), "r"(th));
+  Y = X + m.four_q - T; X = X + T;
+}
+// ---- variant 3: FAST, X' folded into the mad chain:  X' = X + y*w + Q*negq ; Y' = 2X + 4q - X'
+__device__ __forceinline__ void bf3(u64& X, u64& Y, Tw w, const Mod& m) {
+  const unsigned y0 = lo32(Y), y1 = hi32(Y), w0 = lo32(w.w), w1 = hi32(w.w);
+  u64 Q = mulhi_approx(Y, w.wp);
+  const unsigned q0 = lo32(Q), q1 = hi32(Q);
+  u64 t = (u64)y0 * w0 + X; t = (u64)q0 * m.n0 + t;
+  unsigned h = hi32(t);
+  h = y0 * w1 + h; h = y1 * w0 + h; h = q0 * m.n1 + h; h = q1 * m.n0 + h;
+  u64 Xn = join(lo32(t), h);
+  Y = X + X + m.four_q - Xn; X = Xn;
+}
+// ---- variant 4: GENERIC with mad chain and carry-based csub
+__device__ __forceinline__ void bf4(u64& X, u64& Y, Tw w, const Mod& m) {
+  u64 tx = csub(X, m.two_q);
+  u64 T = mad_chain(Y, w.w, __umul64hi(Y, w.wp), m);
+  X = tx + T; Y = tx + m.two_q - T;
+}
+
+template <int V> __device__ __forceinline__ void bf(u64& X, u64& Y, Tw w, const Mod& m) {
+  if (V == 0) bf0(X, Y, w, m); else if (V == 1) bf1(X, Y, w, m); else if (V == 2) bf2(X, Y, w, m);
+  else if (V == 3) bf3(X, Y, w, m); else bf4(X, Y, w, m);
+}
+
+template <int V, int MINB>
+__global__ void __launch_bounds__(256, MINB) kern(u64* out, const Tw* tw, Mod m, int iters) {
+  u64 v[16];
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = (u64)tid * 0x9E3779B97F4A7C15ull + e * 0x1234567ull;
+  Tw w[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) w[g] = tw[(tid + g) & 1023];
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int eb = 3; eb >= 0; --eb) {
+#pragma unroll
+      for (int g = 0; g < (8 >> eb); ++g)
+#pragma unroll
+        for (int l = 0; l < (1 << eb); ++l) {
+          const int e = (g << (eb + 1)) | l;
+          bf<V>(v[e], v[e | (1 << eb)], w[g], m);
+        }
+    }
+    if (V == 1 || V == 2 || V == 3) {  // keep FAST values bounded: mask to 60 bits (cheap, not part of the count)
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] &= (1ull << 60) - 1;
+    }
+  }
+  u64 acc = 0;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc ^= v[e];
+  out[tid] = acc;
+}
+
+template <int V, int MINB> void run(const char* name, u64* out, const Tw* tw, Mod m, int blocks_per_sm) {
+  const int iters = 2000, grid = 148 * blocks_per_sm;
+  kern<V, MINB><<<grid, 256>>>(out, tw, m, 10);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a);
+  kern<V, MINB><<<grid, 256>>>(out, tw, m, iters);
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  double bfl = (double)grid * 256 * iters * 32;
+  int regs = 0; cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern<V, MINB>); regs = fa.numRegs;
+  printf("%-28s blocks/SM %d regs %3d : %8.1f G bfly/s  = %6.3f M NTT(2^16)/s  err=%s\n", name, blocks_per_sm, regs,
+         bfl / ms / 1e6, bfl / ms / 1e3 / 524288.0 / 1e3, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main() {
+  u64* out; Tw* tw; cudaMalloc(&out, 148 * 8 * 256 * 8); cudaMalloc(&tw, 1024 * sizeof(Tw));
+  Tw h[1024]; u64 q = 36028797019488257ull;
+  for (int i = 0; i < 1024; ++i) { h[i].w = (0x9E3779B97F4A7C15ull * (i + 1)) % q; h[i].wp = (u64)(((unsigned __int128)h[i].w << 64) / q); }
+  cudaMemcpy(tw, h, sizeof h, cudaMemcpyHostToDevice);
+  Mod m; m.q = q; m.two_q = 2 * q; m.four_q = 4 * q; m.mu = (u64)(((unsigned __int128)1 << 64) / q);
+  u64 nq = 0 - q; m.n0 = (unsigned)nq; m.n1 = (unsigned)(nq >> 32);
+  for (int bps = 2; bps <= 4; ++bps) {
+    run<0, 2>("v0 generic first", out, tw, m, bps);
+    run<4, 2>("v4 generic madchain", out, tw, m, bps);
+    run<1, 2>("v1 fast lib", out, tw, m, bps);
+    run<2, 2>("v2 fast ptx", out, tw, m, bps);
+    run<3, 2>("v3 fast folded", out, tw, m, bps);
+  }
+  run<1, 3>("v1 fast lib mb3", out, tw, m, 3);
+  run<2, 3>("v2 fast ptx mb3", out, tw, m, 3);
+  run<3, 3>("v3 fast folded mb3", out, tw, m, 3);
+  run<1, 4>("v1 fast lib mb4", out, tw, m, 4);
+  run<2, 4>("v2 fast ptx mb4", out, tw, m, 4);
+  run<3, 4>("v3 fast folded mb4", out, tw, m, 4);
+  return 0;
+}
