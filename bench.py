@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--e2e-batch", type=int, default=None, help="polynomials per GPU for the host-pointer leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-eltwise", action="store_true")
     return ap.parse_args()
 
 
@@ -103,10 +104,28 @@ class ClockSampler:
 
 # ------------------------------------------------------------ reference arm
 def cpu_threads() -> int:
+    """host threads this process can actually run concurrently: the affinity mask
+    capped by the cgroup CPU quota (a container may see 128 CPUs but own 16)."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    quota = None
+    try:  # cgroup v2
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = int(q) / int(period)
+    except (OSError, ValueError):
+        try:  # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / period
+        except (OSError, ValueError):
+            pass
+    if quota:
+        n = max(1, min(n, int(quota + 0.999)))
+    return n
 
 
 def cpu_leg(n, q, threads, polys, reps):
@@ -173,6 +192,24 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------ multi-rank helpers
+def max_over_ranks(value: float, world: int, device="cuda") -> float:
+    """device-timed duration -> max over ranks (NCCL on GPUs, gloo in the CPU test)"""
+    if world <= 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_value(units_per_rank: int, world: int, seconds: float, weak: bool = True, total_units: int = 0) -> float:
+    """units/second of the whole job: weak scaling counts world * units_per_rank"""
+    units = world * units_per_rank if weak else total_units
+    return units / seconds
+
+
 # ----------------------------------------------------------------- b200 arm
 def run_b200_arm(args):
     import numpy as np
@@ -227,12 +264,9 @@ def run_b200_arm(args):
     ms_total = e0.elapsed_time(e1)
     launches = hb.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = max_over_ranks(ms_total, world)
     ms_step = ms_total / args.steps
-    value = world * 2 * batch / (ms_step * 1e-3)
+    value = whole_job_value(2 * batch, world, ms_step * 1e-3)
 
     # ---- roofline of the forward transform (its kernels, events on the launch stream)
     fe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -264,6 +298,35 @@ def run_b200_arm(args):
                 "inv_achieved": alg_bytes / (inv_ms * 1e-3) / 1e9,
                 "butterflies_per_ntt": (n // 2) * args.logn}
 
+    # ---- eltwise kernels (BASELINE configs[2]): algorithmic GB/s at 4096 x 2^16 elements, 60-bit q
+    elt = None
+    if not args.no_eltwise:
+        en = 4096 << 16
+        eq = hb.GeneratePrimes(1, 60, True, 1 << 16)[0]
+        a = torch.randint(0, eq, (en,), dtype=torch.int64, device="cuda", generator=g)
+        b = torch.randint(0, eq, (en,), dtype=torch.int64, device="cuda", generator=g)
+        r = torch.empty_like(a)
+        ops = {
+            "mult_mod": (24, lambda: hb.EltwiseMultMod(r, a, b, en, eq, 1)),
+            "fma_mod": (24, lambda: hb.EltwiseFMAMod(r, a, 123456789, b, en, eq, 1)),
+            "reduce_mod": (16, lambda: hb.EltwiseReduceMod(r, a, en, eq, eq, 1)),
+            "add_mod": (24, lambda: hb.EltwiseAddMod(r, a, b, en, eq)),
+        }
+        elt = {"n": en, "q_bits": 60}
+        for name, (bpe, fn) in ops.items():
+            for _ in range(3):
+                fn()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            s0.record()
+            for _ in range(5):
+                fn()
+            s1.record()
+            torch.cuda.synchronize()
+            gbs = bpe * en * 5 / (s0.elapsed_time(s1) * 1e-3) / 1e9
+            elt[name] = {"GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+        del a, b, r
+
     # ---- end to end through the host-pointer path of the C ABI
     e2e = None
     if not args.no_e2e:
@@ -292,11 +355,8 @@ def run_b200_arm(args):
                 estep()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-            e2e = {"value": world * 2 * eb * esteps / dt, "unit": "NTT/s",
+            dt = max_over_ranks(dt, world)
+            e2e = {"value": whole_job_value(2 * eb * esteps, world, dt), "unit": "NTT/s",
                    "h2d_bytes_per_step": 2 * 8 * n * eb, "d2h_bytes_per_step": 2 * 8 * n * eb,
                    "batch_per_gpu": eb, "steps": esteps, "ms_per_step": 1e3 * dt / esteps,
                    "path": "hexl_b200_ntt_forward/inverse with pinned HOST pointers (library stages H2D/kernel/D2H in 32 MiB chunks on 3 streams)"}
@@ -322,6 +382,7 @@ def run_b200_arm(args):
                        "parallelism": f"{world} x independent shards, no data-path collective",
                        "l2": f"inputs ({8 * n * batch >> 20} MiB per buffer per GPU) exceed the 126 MB L2; no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "eltwise": elt,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -30,6 +30,11 @@
 
 #include "internal.h"
 
+// build-time tuning knobs (hexl_b200/build.py: HEXL_B200_BUILD_FLAGS)
+#ifndef HEXL_B200_TW_PREFETCH
+#define HEXL_B200_TW_PREFETCH 0
+#endif
+
 namespace hexl_b200 {
 namespace {
 
@@ -45,7 +50,7 @@ namespace {
 //    states them (ntt-default.hpp:28-42,112-125): forward values stay in [0,4q),
 //    inverse values in [0,2q), one conditional subtraction per butterfly.
 //
-//  FAST (q < 2^56): the 2^64/q >= 256 of headroom replaces the per-butterfly
+//  FAST (2^32 <= q < 2^56): the 2^64/q >= 256 of headroom replaces the per-butterfly
 //    conditional subtractions.  The Shoup quotient is estimated from three 32x32
 //    partial products (no lo*lo term, no carry between the middle terms: low by
 //    at most 2), so a twiddle product lands in [0,4q).  Forward: X' = X + T,
@@ -70,7 +75,34 @@ struct Mod {
 
 __device__ __forceinline__ unsigned lo32(u64 x) { return (unsigned)x; }
 __device__ __forceinline__ unsigned hi32(u64 x) { return (unsigned)(x >> 32); }
-__device__ __forceinline__ u64 join(unsigned lo, unsigned hi) { return ((u64)hi << 32) | lo; }
+__device__ __forceinline__ u64 join(unsigned lo, unsigned hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void split(u64 x, unsigned& lo, unsigned& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x));
+}
+// The multiply primitives are pinned with PTX so that ptxas keeps them on the
+// FMA-heavy pipe (IMAD / IMAD.WIDE, one every 2 cycles per scheduler) instead of
+// turning accumulations into 64-bit IADD3 pairs plus register-pair moves on the
+// ALU pipe, which is the scarcer resource in these kernels (tools/inst_bench.cu;
+// IMAD.HI is ~3x slower than IMAD.WIDE and is never used).
+__device__ __forceinline__ u64 mul_wide(unsigned a, unsigned b) {
+  u64 r;
+  asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ u64 mad_wide(unsigned a, unsigned b, u64 c) {
+  u64 r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ unsigned mad_lo(unsigned a, unsigned b, unsigned c) {
+  unsigned r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
 
 __device__ __forceinline__ Twiddle ld_tw(const Twiddle* p) {
   const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
@@ -80,24 +112,30 @@ __device__ __forceinline__ Twiddle ld_tw(const Twiddle* p) {
   return t;
 }
 
-// floor(a*b / 2^64) - {0,1,2}: a1*b1 + hi32(a1*b0) + hi32(a0*b1)
+// floor(a*b / 2^64) - {0,1,2}: a1*b1 + hi32(a1*b0) + hi32(a0*b1); the two high
+// halves are folded in with multiply-by-one wide mads (no ALU work at all).
 __device__ __forceinline__ u64 mulhi_approx(u64 a, u64 b) {
-  const unsigned a0 = lo32(a), a1 = hi32(a), b0 = lo32(b), b1 = hi32(b);
-  return (u64)a1 * b1 + (u64)__umulhi(a1, b0) + (u64)__umulhi(a0, b1);
+  unsigned a0, a1, b0, b1;
+  split(a, a0, a1);
+  split(b, b0, b1);
+  u64 Q = mul_wide(a1, b1);
+  Q = mad_wide(hi32(mul_wide(a1, b0)), 1u, Q);
+  Q = mad_wide(hi32(mul_wide(a0, b1)), 1u, Q);
+  return Q;
 }
 
-// low 64 bits of c + x*w + Q*(2^64 - q) as one chain of 2 wide and 4 narrow IMADs
+// low 64 bits of x*w + Q*(2^64 - q): 2 wide and 4 narrow IMADs, no adds
 __device__ __forceinline__ u64 mad_chain(u64 x, u64 w, u64 Q, const Mod& m) {
-  const unsigned x0 = lo32(x), x1 = hi32(x), w0 = lo32(w), w1 = hi32(w);
-  const unsigned q0 = lo32(Q), q1 = hi32(Q);
-  u64 t = (u64)x0 * w0;
-  t = (u64)q0 * m.n0 + t;
-  unsigned h = hi32(t);
-  h = x0 * w1 + h;
-  h = x1 * w0 + h;
-  h = q0 * m.n1 + h;
-  h = q1 * m.n0 + h;
-  return join(lo32(t), h);
+  unsigned x0, x1, w0, w1, q0, q1, t0, t1;
+  split(x, x0, x1);
+  split(w, w0, w1);
+  split(Q, q0, q1);
+  split(mad_wide(q0, m.n0, mul_wide(x0, w0)), t0, t1);
+  t1 = mad_lo(x0, w1, t1);
+  t1 = mad_lo(x1, w0, t1);
+  t1 = mad_lo(q0, m.n1, t1);
+  t1 = mad_lo(q1, m.n0, t1);
+  return join(t0, t1);
 }
 
 // x*w mod q, lazily: exact quotient -> [0,2q); approximate quotient -> [0,4q)
@@ -110,15 +148,24 @@ __device__ __forceinline__ u64 mul_tw_exact(u64 x, const Twiddle w, const Mod& m
   return mad_chain(x, w.w, mulhi(x, w.wp), m);
 }
 
-// any 64-bit value -> [0,2q):  x - floor(x*mu/2^64)*q
+// any 64-bit value -> [0,2q):  x - floor(x*mu/2^64)*q, mu = floor(2^64/q)
 __device__ __forceinline__ u64 barrett_lazy(u64 x, const Mod& m) {
-  const u64 Q = mulhi(x, m.mu);
-  const unsigned q0 = lo32(Q), q1 = hi32(Q);
-  u64 t = (u64)q0 * m.n0 + x;
-  unsigned h = hi32(t);
-  h = q0 * m.n1 + h;
-  h = q1 * m.n0 + h;
-  return join(lo32(t), h);
+  unsigned q0, q1, t0, t1;
+  split(mulhi(x, m.mu), q0, q1);
+  split(mad_wide(q0, m.n0, x), t0, t1);
+  t1 = mad_lo(q0, m.n1, t1);
+  t1 = mad_lo(q1, m.n0, t1);
+  return join(t0, t1);
+}
+// Same for q >= 2^32, where mu < 2^32 and the quotient is a single 32-bit word.
+__device__ __forceinline__ u64 barrett_lazy_bigq(u64 x, const Mod& m) {
+  unsigned x0, x1, t0, t1;
+  split(x, x0, x1);
+  const unsigned mu0 = lo32(m.mu);
+  const u64 s = mad_wide(hi32(mul_wide(x0, mu0)), 1u, mul_wide(x1, mu0));  // floor(x*mu / 2^32)
+  const unsigned Q = hi32(s);
+  split(mad_wide(Q, m.n0, x), t0, t1);
+  return join(t0, mad_lo(Q, m.n1, t1));
 }
 
 // ----------------------------------------------------------------- butterflies
@@ -165,7 +212,7 @@ __device__ __forceinline__ void inv_bfly_last(u64& X, u64& Y, const Twiddle inv_
 template <int MODE>
 __device__ __forceinline__ u64 fwd_out(u64 v, const Mod& m, int out_mf) {
   if (MODE == kFast) {
-    v = barrett_lazy(v, m);  // [0,2q), fine for out_mf == 4 as well
+    v = barrett_lazy_bigq(v, m);  // [0,2q), fine for out_mf == 4 as well
     return out_mf == 1 ? csub(v, m.q) : v;
   }
   return out_mf == 1 ? csub(csub(v, m.two_q), m.q) : v;
@@ -191,7 +238,7 @@ __host__ __device__ constexpr int inv_stage_cover(int s) { return kFastBound << 
 template <int K, int NSLOTS, int E = 0>
 __device__ __forceinline__ void inv_pass_fixup(u64* v, const Mod& m) {
   if constexpr (E < NSLOTS) {
-    if constexpr (inv_slot_bound(K, E & ((1 << K) - 1)) > kFastBound) v[E] = barrett_lazy(v[E], m);
+    if constexpr (inv_slot_bound(K, E & ((1 << K) - 1)) > kFastBound) v[E] = barrett_lazy_bigq(v[E], m);
     inv_pass_fixup<K, NSLOTS, E + 1>(v, m);
   }
 }
@@ -216,34 +263,58 @@ template <int MODE, int LOGC, int LB, int HB, int LOB, bool FWD>
 __device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
                                            const Twiddle* __restrict__ tw, const Mod& m, bool fold,
                                            Twiddle inv_n, Twiddle inv_n_w) {
+  // Twiddles of stage k+1 are requested before the butterflies of stage k run
+  // (HEXL_B200_TW_PREFETCH), so their L2 latency hides behind a stage of math.
+  Twiddle wc[8], wn[8];
+  auto stage_node0 = [&](int step) {
+    const int beta = FWD ? HB - step : LOB + step;
+    return (base << (LOGC - 1 - beta)) + ((u64)(u >> LB) << (LB + 3 - beta));
+  };
+#if HEXL_B200_TW_PREFETCH
+  {
+    const int eb0 = (FWD ? HB : LOB) - LB;
+#pragma unroll
+    for (int g = 0; g < (8 >> eb0); ++g) wc[g] = ld_tw(tw + stage_node0(0) + g);
+  }
+#endif
 #pragma unroll
   for (int step = 0; step <= HB - LOB; ++step) {
     const int beta = FWD ? HB - step : LOB + step;  // index bit of this stage
     const int eb = beta - LB;                       // register bit
     const int sp = LOGC - 1 - beta;                 // stage number inside the row
-    const u64 node0 = (base << sp) + ((u64)(u >> LB) << (LB + 3 - beta));
     // FAST inverse: multiple of q covering every Y of this stage (GENERIC: 2q)
     const u64 cq = (!FWD && MODE == kFast) ? (u64)inv_stage_cover(step) * m.q : m.two_q;
+#if HEXL_B200_TW_PREFETCH
+    if (step < HB - LOB) {
+      const int ebn = (FWD ? beta - 1 : beta + 1) - LB;
+#pragma unroll
+      for (int g = 0; g < (8 >> ebn); ++g) wn[g] = ld_tw(tw + stage_node0(step + 1) + g);
+    }
+#else
+#pragma unroll
+    for (int g = 0; g < (8 >> eb); ++g) wc[g] = ld_tw(tw + stage_node0(step) + g);
+#endif
     if (!FWD && sp == 0 && fold) {
       // root stage of the whole transform: one group, N^-1 folded in
 #pragma unroll
       for (int l = 0; l < (1 << eb); ++l) inv_bfly_last(v[l], v[l | (1 << eb)], inv_n, inv_n_w, m, cq);
     } else {
-      Twiddle w[8];
-#pragma unroll
-      for (int g = 0; g < (8 >> eb); ++g) w[g] = ld_tw(tw + node0 + g);
 #pragma unroll
       for (int g = 0; g < (8 >> eb); ++g) {
 #pragma unroll
         for (int l = 0; l < (1 << eb); ++l) {
           const int e = (g << (eb + 1)) | l;
           if (FWD)
-            fwd_bfly<MODE>(v[e], v[e | (1 << eb)], w[g], m);
+            fwd_bfly<MODE>(v[e], v[e | (1 << eb)], wc[g], m);
           else
-            inv_bfly<MODE>(v[e], v[e | (1 << eb)], w[g], m, cq);
+            inv_bfly<MODE>(v[e], v[e | (1 << eb)], wc[g], m, cq);
         }
       }
     }
+#if HEXL_B200_TW_PREFETCH
+#pragma unroll
+    for (int g = 0; g < 8; ++g) wc[g] = wn[g];
+#endif
   }
   if (!FWD && MODE == kFast && !(fold && LOGC - 1 - HB == 0)) inv_pass_fixup<HB - LOB + 1, 16>(v, m);
 }
@@ -290,7 +361,7 @@ __device__ __forceinline__ void inv_passes(u64 (&v)[16], u64* srow, unsigned u, 
 }
 
 #ifndef HEXL_B200_ROW_MIN_BLOCKS
-#define HEXL_B200_ROW_MIN_BLOCKS 2
+#define HEXL_B200_ROW_MIN_BLOCKS 3
 #endif
 
 template <int LOGC>
@@ -497,7 +568,7 @@ int pick_row_log(int log_n) {
 
 int pick_mode(u64 q) {
   static const bool force_generic = env_int("HEXL_B200_FORCE_GENERIC", 0) != 0;
-  return (!force_generic && q < kFastModulusLimit) ? kFast : kGeneric;
+  return (!force_generic && q < kFastModulusLimit && q >= (1ull << 32)) ? kFast : kGeneric;
 }
 
 Mod make_mod(const NttDeviceTables& t) {

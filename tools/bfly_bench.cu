@@ -84,9 +84,56 @@ __device__ __forceinline__ void bf4(u64& X, u64& Y, Tw w, const Mod& m) {
   X = tx + T; Y = tx + m.two_q - T;
 }
 
+// ---- variant 5: FAST as in the library now (PTX-pinned wide/narrow mads, no IMAD.HI)
+__device__ __forceinline__ void split(u64 x, unsigned& lo, unsigned& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x)); }
+__device__ __forceinline__ u64 join2(unsigned lo, unsigned hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ u64 mulhi_approx5(u64 a, u64 b) {
+  unsigned a0, a1, b0, b1; split(a, a0, a1); split(b, b0, b1);
+  u64 Q = mulwide(a1, b1);
+  Q = madwide(hi32(mulwide(a1, b0)), 1u, Q);
+  Q = madwide(hi32(mulwide(a0, b1)), 1u, Q);
+  return Q;
+}
+__device__ __forceinline__ u64 mad_chain5(u64 x, u64 w, u64 Q, const Mod& m) {
+  unsigned x0, x1, w0, w1, q0, q1, t0, t1;
+  split(x, x0, x1); split(w, w0, w1); split(Q, q0, q1);
+  split(madwide(q0, m.n0, mulwide(x0, w0)), t0, t1);
+  t1 = madlo(x0, w1, t1); t1 = madlo(x1, w0, t1); t1 = madlo(q0, m.n1, t1); t1 = madlo(q1, m.n0, t1);
+  return join2(t0, t1);
+}
+__device__ __forceinline__ void bf5(u64& X, u64& Y, Tw w, const Mod& m) {
+  u64 T = mad_chain5(Y, w.w, mulhi_approx5(Y, w.wp), m);
+  Y = X + m.four_q - T; X = X + T;
+}
+// ---- variant 6: exact mulhi (compiler's __umul64hi) + pinned mad chain, no csub (FAST-exact)
+__device__ __forceinline__ void bf6(u64& X, u64& Y, Tw w, const Mod& m) {
+  u64 T = mad_chain5(Y, w.w, __umul64hi(Y, w.wp), m);
+  Y = X + m.two_q - T; X = X + T;
+}
+// ---- variant 7: multiplies only (no adds for X',Y'): how fast can the 9-IMAD core go
+__device__ __forceinline__ void bf7(u64& X, u64& Y, Tw w, const Mod& m) {
+  u64 T = mad_chain5(Y, w.w, mulhi_approx5(Y, w.wp), m);
+  Y = T ^ X; X = T;
+}
+// ---- variant 8: adds only (no multiplies)
+__device__ __forceinline__ void bf8(u64& X, u64& Y, Tw w, const Mod& m) {
+  u64 T = Y ^ w.w;
+  Y = X + m.four_q - T; X = X + T;
+}
+
 template <int V> __device__ __forceinline__ void bf(u64& X, u64& Y, Tw w, const Mod& m) {
+  if (V == 5) { bf5(X, Y, w, m); return; } if (V == 6) { bf6(X, Y, w, m); return; }
+  if (V == 7) { bf7(X, Y, w, m); return; } if (V == 8) { bf8(X, Y, w, m); return; }
   if (V == 0) bf0(X, Y, w, m); else if (V == 1) bf1(X, Y, w, m); else if (V == 2) bf2(X, Y, w, m);
   else if (V == 3) bf3(X, Y, w, m); else bf4(X, Y, w, m);
+}
+
+template <int V, int EB>
+__device__ __forceinline__ void stage(u64 (&v)[16], const Tw (&w)[8], const Mod& m) {
+#pragma unroll
+  for (int g = 0; g < (8 >> EB); ++g)
+#pragma unroll
+    for (int l = 0; l < (1 << EB); ++l) bf<V>(v[(g << (EB + 1)) | l], v[((g << (EB + 1)) | l) | (1 << EB)], w[g], m);
 }
 
 template <int V, int MINB>
@@ -99,17 +146,8 @@ __global__ void __launch_bounds__(256, MINB) kern(u64* out, const Tw* tw, Mod m,
 #pragma unroll
   for (int g = 0; g < 8; ++g) w[g] = tw[(tid + g) & 1023];
   for (int it = 0; it < iters; ++it) {
-#pragma unroll
-    for (int eb = 3; eb >= 0; --eb) {
-#pragma unroll
-      for (int g = 0; g < (8 >> eb); ++g)
-#pragma unroll
-        for (int l = 0; l < (1 << eb); ++l) {
-          const int e = (g << (eb + 1)) | l;
-          bf<V>(v[e], v[e | (1 << eb)], w[g], m);
-        }
-    }
-    if (V == 1 || V == 2 || V == 3) {  // keep FAST values bounded: mask to 60 bits (cheap, not part of the count)
+    stage<V, 3>(v, w, m); stage<V, 2>(v, w, m); stage<V, 1>(v, w, m); stage<V, 0>(v, w, m);
+    if (V != 0 && V != 4) {  // keep FAST values bounded: mask to 60 bits (cheap, not part of the count)
 #pragma unroll
       for (int e = 0; e < 16; ++e) v[e] &= (1ull << 60) - 1;
     }
@@ -130,8 +168,9 @@ template <int V, int MINB> void run(const char* name, u64* out, const Tw* tw, Mo
   float ms; cudaEventElapsedTime(&ms, a, b);
   double bfl = (double)grid * 256 * iters * 32;
   int regs = 0; cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern<V, MINB>); regs = fa.numRegs;
-  printf("%-28s blocks/SM %d regs %3d : %8.1f G bfly/s  = %6.3f M NTT(2^16)/s  err=%s\n", name, blocks_per_sm, regs,
-         bfl / ms / 1e6, bfl / ms / 1e3 / 524288.0 / 1e3, cudaGetErrorString(cudaGetLastError()));
+  printf("%-28s blocks/SM %d regs %3d : %8.1f G bfly/s = %6.3f M NTT(2^16)/s = %5.1f SMSP-cycles per warp-bfly  %s\n", name,
+         blocks_per_sm, regs, bfl / ms / 1e6, bfl / ms / 1e6 / 524288.0 * 1e3, 592.0 * 1.965e9 / (bfl / ms * 1e3 / 32),
+         cudaGetErrorString(cudaGetLastError()));
 }
 
 int main() {
@@ -141,18 +180,17 @@ int main() {
   cudaMemcpy(tw, h, sizeof h, cudaMemcpyHostToDevice);
   Mod m; m.q = q; m.two_q = 2 * q; m.four_q = 4 * q; m.mu = (u64)(((unsigned __int128)1 << 64) / q);
   u64 nq = 0 - q; m.n0 = (unsigned)nq; m.n1 = (unsigned)(nq >> 32);
-  for (int bps = 2; bps <= 4; ++bps) {
-    run<0, 2>("v0 generic first", out, tw, m, bps);
-    run<4, 2>("v4 generic madchain", out, tw, m, bps);
-    run<1, 2>("v1 fast lib", out, tw, m, bps);
-    run<2, 2>("v2 fast ptx", out, tw, m, bps);
-    run<3, 2>("v3 fast folded", out, tw, m, bps);
+  run<0, 2>("v0 generic first", out, tw, m, 2);
+  run<4, 2>("v4 generic madchain", out, tw, m, 2);
+  run<1, 2>("v1 fast IMAD.HI", out, tw, m, 2);
+  for (int bps = 2; bps <= 3; ++bps) {
+    run<5, 2>("v5 fast pinned (lib)", out, tw, m, bps);
+    run<6, 2>("v6 fast exact-mulhi", out, tw, m, bps);
+    run<7, 2>("v7 multiplies only", out, tw, m, bps);
+    run<8, 2>("v8 adds only", out, tw, m, bps);
   }
-  run<1, 3>("v1 fast lib mb3", out, tw, m, 3);
-  run<2, 3>("v2 fast ptx mb3", out, tw, m, 3);
-  run<3, 3>("v3 fast folded mb3", out, tw, m, 3);
-  run<1, 4>("v1 fast lib mb4", out, tw, m, 4);
-  run<2, 4>("v2 fast ptx mb4", out, tw, m, 4);
-  run<3, 4>("v3 fast folded mb4", out, tw, m, 4);
+  run<5, 3>("v5 mb3", out, tw, m, 3);
+  run<6, 3>("v6 mb3", out, tw, m, 3);
+  run<7, 3>("v7 mb3", out, tw, m, 3);
   return 0;
 }
