@@ -319,14 +319,22 @@ __device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
   if (!FWD && MODE == kFast && !(fold && LOGC - 1 - HB == 0)) inv_pass_fixup<HB - LOB + 1, 16>(v, m);
 }
 
+// Transpose between two register layouts through shared memory.  The exchange
+// only permutes thread-id bits [min(LB), max(LB)), so when max(LB) <= 5 every
+// value stays inside one warp and __syncwarp() replaces the CTA barrier.  No
+// barrier is needed after the reads: the next exchange writes exactly the
+// addresses this thread has just read (same layout), which nobody else touches.
 template <int LB_FROM, int LB_TO>
 __device__ __forceinline__ void smem_exchange(u64 (&v)[16], u64* srow, unsigned u) {
+  constexpr bool kWarpLocal = (LB_FROM > LB_TO ? LB_FROM : LB_TO) <= 5;
 #pragma unroll
   for (int e = 0; e < 16; ++e) srow[swz(reg_index<LB_FROM>(u, e))] = v[e];
-  __syncthreads();
+  if (kWarpLocal)
+    __syncwarp();
+  else
+    __syncthreads();
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = srow[swz(reg_index<LB_TO>(u, e))];
-  __syncthreads();
 }
 
 // Forward passes after pass 0: register bits move down by 4 per pass, clamped at 0.
@@ -400,16 +408,13 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS, RowCfg<LOGC>::MIN_BLOCK
   // registers now hold 16 consecutive coefficients per thread (LB = 0)
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = fwd_out<MODE>(v[e], m, out_mf);
-  if constexpr (LOGC > 4) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) srow[swz(reg_index<0>(u, e))] = v[e];
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = srow[swz(reg_index<LB0>(u, e))];
-  }
+  // store layout: 16 lanes write one 128-byte line per instruction; reaching it
+  // from LB = 0 is a warp-local exchange
+  constexpr int LB_OUT = LB0 < 4 ? LB0 : 4;
+  if constexpr (LOGC > 4) smem_exchange<0, LB_OUT>(v, srow, u);
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) __stcs(out + reg_index<LB0>(u, e), v[e]);
+    for (int e = 0; e < 16; ++e) __stcs(out + reg_index<LB_OUT>(u, e), v[e]);
   }
 }
 
@@ -431,17 +436,11 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS, RowCfg<LOGC>::MIN_BLOCK
 
   u64 v[16];
   constexpr int LB0 = LOGC - 4;
+  constexpr int LB_IN = LB0 < 4 ? LB0 : 4;  // 16 lanes read one 128-byte line per instruction
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = __ldcs(in + reg_index<LB0>(u, e));
-  if constexpr (LOGC > 4) {
-    // coalesced load layout -> 16 consecutive coefficients per thread
-#pragma unroll
-    for (int e = 0; e < 16; ++e) srow[swz(reg_index<LB0>(u, e))] = v[e];
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = srow[swz(reg_index<0>(u, e))];
-    __syncthreads();
-  }
+  for (int e = 0; e < 16; ++e) v[e] = __ldcs(in + reg_index<LB_IN>(u, e));
+  // -> 16 consecutive coefficients per thread (warp-local exchange)
+  if constexpr (LOGC > 4) smem_exchange<LB_IN, 0>(v, srow, u);
   inv_passes<MODE, LOGC, Cfg::PASSES - 1>(v, srow, u, base, tw, m, fold != 0, inv_n, inv_n_w);
   // last pass left the registers in the coalesced layout (LB = LOGC-4)
   if (active) {

@@ -44,6 +44,7 @@ class Model:
         self.fwd = np.array(fwd_tree, dtype=object)
         self.inv = np.array(inv_tree, dtype=object)
         self.inv_n, self.inv_n_w = inv_n, inv_n_w
+        self.cta_exchanges = 0
 
     # ---- butterflies on object arrays (fully reduced)
     def _fwd_bfly(self, X, Y, w):
@@ -77,18 +78,26 @@ class Model:
 
     def exchange(self, v, u, lb_from, lb_to, c):
         smem = np.empty(c, dtype=object)
+        writer = np.full(c, -1, dtype=int)
         written = np.zeros(c, dtype=int)
         for e in range(16):
             idx = swz(reg_index(u, e, lb_from))
             smem[idx] = v[e]
+            writer[idx] = u
             np.add.at(written, idx, 1)
         assert (written == 1).all(), "smem write map is not a permutation"
         read = np.zeros(c, dtype=int)
+        warp_local = True
         for e in range(16):
             idx = swz(reg_index(u, e, lb_to))
             v[e] = smem[idx]
             np.add.at(read, idx, 1)
+            warp_local &= bool(((writer[idx] >> 5) == (u >> 5)).all())
         assert (read == 1).all(), "smem read map is not a permutation"
+        # the kernel uses __syncwarp() instead of __syncthreads() exactly when max(lb) <= 5
+        if max(lb_from, lb_to) <= 5:
+            assert warp_local, (lb_from, lb_to)
+        self.cta_exchanges += 0 if max(lb_from, lb_to) <= 5 else 1
 
     @staticmethod
     def bank_conflict_degree(u, e, lb):
@@ -106,9 +115,10 @@ class Model:
         t = c // 16
         u = np.arange(t)
         lb0 = logc - 4
-        v = [data[reg_index(u, e, lb0)].copy() for e in range(16)]
+        lb_io = min(lb0, 4)  # 128-byte-line load/store layout of the inverse input / forward output
         passes = (logc + 3) // 4
         if fwd:
+            v = [data[reg_index(u, e, lb0)].copy() for e in range(16)]
             self.reg_stages(v, u, base, logc, lb0, logc - 1, lb0, True, False)
             prev_lb = lb0
             for p in range(1, passes + 1):
@@ -120,10 +130,12 @@ class Model:
                 self.reg_stages(v, u, base, logc, lb, hb, lb, True, False)
                 prev_lb = lb
             if logc > 4:
-                self.exchange(v, u, 0, lb0, c)
+                self.exchange(v, u, 0, lb_io, c)
+            out_lb = lb_io
         else:
+            v = [data[reg_index(u, e, lb_io)].copy() for e in range(16)]
             if logc > 4:
-                self.exchange(v, u, lb0, 0, c)
+                self.exchange(v, u, lb_io, 0, c)
             for p in range(passes - 1, -1, -1):
                 hb = logc - 4 * p - 1
                 lb = max(hb - 3, 0)
@@ -132,9 +144,10 @@ class Model:
                     nhb = logc - 4 * (p - 1) - 1
                     nlb = max(nhb - 3, 0)
                     self.exchange(v, u, lb, nlb, c)
+            out_lb = lb0
         out = np.empty(c, dtype=object)
         for e in range(16):
-            out[reg_index(u, e, lb0)] = v[e]
+            out[reg_index(u, e, out_lb)] = v[e]
         return out
 
     def col_pass(self, data, logr, log_s, fwd, fold):

@@ -34,7 +34,27 @@ def test_model_matches_oracle(port, logn, logc):
     x = uniform_below(logn * 100 + logc, n, q)
     y = port.ntt_forward(x, n, q)
     assert [int(v) for v in m.forward(x, logc)] == [int(v) for v in y]
+    rows = n >> logc
+    assert m.cta_exchanges == rows * sum(1 for lb in _fwd_exchange_lbs(logc) if lb > 5)
     assert [int(v) for v in m.inverse(y, logc)] == [int(v) for v in x]
+
+
+def _fwd_exchange_lbs(logc):
+    """max(LB) of every exchange of the forward row kernel (CTA barrier iff > 5)"""
+    lbs, prev, p = [], logc - 4, 1
+    while logc - 4 * p - 1 >= 0:
+        lb = max(logc - 4 * p - 4, 0)
+        lbs.append(max(prev, lb))
+        prev, p = lb, p + 1
+    if logc > 4:
+        lbs.append(max(0, min(logc - 4, 4)))
+    return lbs
+
+
+def test_one_cta_barrier_per_4096_row():
+    assert [lb for lb in _fwd_exchange_lbs(12) if lb > 5] == [8]
+    assert [lb for lb in _fwd_exchange_lbs(13) if lb > 5] == [9]
+    assert [lb for lb in _fwd_exchange_lbs(10) if lb > 5] == [6]
 
 
 def test_col_pass_plan():
