@@ -30,11 +30,6 @@
 
 #include "internal.h"
 
-// build-time tuning knobs (hexl_b200/build.py: HEXL_B200_BUILD_FLAGS)
-#ifndef HEXL_B200_TW_PREFETCH
-#define HEXL_B200_TW_PREFETCH 0
-#endif
-
 namespace hexl_b200 {
 namespace {
 
@@ -259,24 +254,48 @@ __device__ __forceinline__ unsigned reg_index(unsigned u, int e) {
 
 // Butterfly stages on row-local index bits HB..LOB (all inside [LB, LB+3]).
 // FWD: bits descend (CT).  INV: bits ascend (GS), LOB == LB.
+// Sub-tree twiddle tables in shared memory.  A full 4-stage pass whose register
+// bits sit at LB runs, for thread u, the radix-16 sub-tree rooted at node
+// (base << d) + (u >> LB), d = LOGC - LB - 4.  The first two passes of a row have
+// d = 0 (one root) and d = 4 (16 roots): their 17 x 15 twiddles are fetched once
+// per row by a cooperative load and then read with LDS (tens of cycles) instead
+// of 15 dependent-latency L2 loads per thread per pass.  Layout: 16 entries per
+// root, local node l = 2^s + i at slot l; root table 0 first, then the 16 tables
+// of depth 4.
+constexpr int kRowTwEntries = 17 * 16;
+template <int LOGC, int LB, int HB, int LOB>
+struct PassTw {
+  static constexpr int kDepth = LOGC - LB - 4;
+  static constexpr bool kShared = LOGC >= 8 && (HB - LOB) == 3 && (kDepth == 0 || kDepth == 4);
+  static constexpr int kOffset = kDepth == 0 ? 0 : 16;
+};
+
+template <int LOGC>
+__device__ __forceinline__ void load_row_twiddles(Twiddle* stab, unsigned u, u64 base,
+                                                  const Twiddle* __restrict__ tw) {
+  constexpr int T = (1 << LOGC) / 16;
+  for (int idx = u; idx < kRowTwEntries; idx += T) {
+    const int l = idx & 15;
+    if (l == 0) continue;
+    const u64 root = idx < 16 ? base : (base << 4) + ((idx - 16) >> 4);
+    const int s = 31 - __clz(l);
+    stab[idx] = ld_tw(tw + (root << s) + (l - (1 << s)));
+  }
+}
+
+// Butterfly stages on row-local index bits HB..LOB (all inside [LB, LB+3]).
+// FWD: bits descend (CT).  INV: bits ascend (GS), LOB == LB.
 template <int MODE, int LOGC, int LB, int HB, int LOB, bool FWD>
 __device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
-                                           const Twiddle* __restrict__ tw, const Mod& m, bool fold,
-                                           Twiddle inv_n, Twiddle inv_n_w) {
-  // Twiddles of stage k+1 are requested before the butterflies of stage k run
-  // (HEXL_B200_TW_PREFETCH), so their L2 latency hides behind a stage of math.
-  Twiddle wc[8], wn[8];
+                                           const Twiddle* __restrict__ tw, const Twiddle* stab,
+                                           const Mod& m, bool fold, Twiddle inv_n, Twiddle inv_n_w) {
+  using PT = PassTw<LOGC, LB, HB, LOB>;
+  const Twiddle* sroot = stab + PT::kOffset + ((u >> LB) << 4);  // this thread's sub-tree table
+  Twiddle wc[8];
   auto stage_node0 = [&](int step) {
     const int beta = FWD ? HB - step : LOB + step;
     return (base << (LOGC - 1 - beta)) + ((u64)(u >> LB) << (LB + 3 - beta));
   };
-#if HEXL_B200_TW_PREFETCH
-  {
-    const int eb0 = (FWD ? HB : LOB) - LB;
-#pragma unroll
-    for (int g = 0; g < (8 >> eb0); ++g) wc[g] = ld_tw(tw + stage_node0(0) + g);
-  }
-#endif
 #pragma unroll
   for (int step = 0; step <= HB - LOB; ++step) {
     const int beta = FWD ? HB - step : LOB + step;  // index bit of this stage
@@ -284,21 +303,18 @@ __device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
     const int sp = LOGC - 1 - beta;                 // stage number inside the row
     // FAST inverse: multiple of q covering every Y of this stage (GENERIC: 2q)
     const u64 cq = (!FWD && MODE == kFast) ? (u64)inv_stage_cover(step) * m.q : m.two_q;
-#if HEXL_B200_TW_PREFETCH
-    if (step < HB - LOB) {
-      const int ebn = (FWD ? beta - 1 : beta + 1) - LB;
-#pragma unroll
-      for (int g = 0; g < (8 >> ebn); ++g) wn[g] = ld_tw(tw + stage_node0(step + 1) + g);
-    }
-#else
-#pragma unroll
-    for (int g = 0; g < (8 >> eb); ++g) wc[g] = ld_tw(tw + stage_node0(step) + g);
-#endif
     if (!FWD && sp == 0 && fold) {
       // root stage of the whole transform: one group, N^-1 folded in
 #pragma unroll
       for (int l = 0; l < (1 << eb); ++l) inv_bfly_last(v[l], v[l | (1 << eb)], inv_n, inv_n_w, m, cq);
     } else {
+#pragma unroll
+      for (int g = 0; g < (8 >> eb); ++g) {
+        if (PT::kShared)
+          wc[g] = sroot[(8 >> eb) + g];             // local node 2^s' + g, s' = 3 - eb
+        else
+          wc[g] = ld_tw(tw + stage_node0(step) + g);
+      }
 #pragma unroll
       for (int g = 0; g < (8 >> eb); ++g) {
 #pragma unroll
@@ -311,10 +327,6 @@ __device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
         }
       }
     }
-#if HEXL_B200_TW_PREFETCH
-#pragma unroll
-    for (int g = 0; g < 8; ++g) wc[g] = wn[g];
-#endif
   }
   if (!FWD && MODE == kFast && !(fold && LOGC - 1 - HB == 0)) inv_pass_fixup<HB - LOB + 1, 16>(v, m);
 }
@@ -340,31 +352,31 @@ __device__ __forceinline__ void smem_exchange(u64 (&v)[16], u64* srow, unsigned 
 // Forward passes after pass 0: register bits move down by 4 per pass, clamped at 0.
 template <int MODE, int LOGC, int PASS>
 __device__ __forceinline__ void fwd_passes(u64 (&v)[16], u64* srow, unsigned u, u64 base,
-                                           const Twiddle* tw, const Mod& m) {
+                                           const Twiddle* tw, const Twiddle* stab, const Mod& m) {
   constexpr int PREV_LB = (LOGC - 4 * PASS) > 0 ? (LOGC - 4 * PASS) : 0;
   constexpr int HB = LOGC - 4 * PASS - 1;  // highest index bit not yet processed
   if constexpr (HB >= 0) {
     constexpr int LB = (HB - 3) > 0 ? (HB - 3) : 0;
     smem_exchange<PREV_LB, LB>(v, srow, u);
-    reg_stages<MODE, LOGC, LB, HB, LB, true>(v, u, base, tw, m, false, Twiddle{}, Twiddle{});
-    fwd_passes<MODE, LOGC, PASS + 1>(v, srow, u, base, tw, m);
+    reg_stages<MODE, LOGC, LB, HB, LB, true>(v, u, base, tw, stab, m, false, Twiddle{}, Twiddle{});
+    fwd_passes<MODE, LOGC, PASS + 1>(v, srow, u, base, tw, stab, m);
   }
 }
 
 // Inverse passes: mirror image.  PASS counts down; pass P-1 is done first.
 template <int MODE, int LOGC, int PASS>
 __device__ __forceinline__ void inv_passes(u64 (&v)[16], u64* srow, unsigned u, u64 base,
-                                           const Twiddle* tw, const Mod& m, bool fold, Twiddle inv_n,
-                                           Twiddle inv_n_w) {
+                                           const Twiddle* tw, const Twiddle* stab, const Mod& m, bool fold,
+                                           Twiddle inv_n, Twiddle inv_n_w) {
   // forward pass PASS handled bits HB..LB; the inverse handles the same bits ascending
   constexpr int HB = LOGC - 4 * PASS - 1;
   constexpr int LB = (HB - 3) > 0 ? (HB - 3) : 0;
-  reg_stages<MODE, LOGC, LB, HB, LB, false>(v, u, base, tw, m, fold, inv_n, inv_n_w);
+  reg_stages<MODE, LOGC, LB, HB, LB, false>(v, u, base, tw, stab, m, fold, inv_n, inv_n_w);
   if constexpr (PASS > 0) {
     constexpr int NHB = LOGC - 4 * (PASS - 1) - 1;
     constexpr int NLB = (NHB - 3) > 0 ? (NHB - 3) : 0;
     smem_exchange<LB, NLB>(v, srow, u);
-    inv_passes<MODE, LOGC, PASS - 1>(v, srow, u, base, tw, m, fold, inv_n, inv_n_w);
+    inv_passes<MODE, LOGC, PASS - 1>(v, srow, u, base, tw, stab, m, fold, inv_n, inv_n_w);
   }
 }
 
@@ -379,9 +391,84 @@ struct RowCfg {
   static constexpr int ROWS = T >= 256 ? 1 : 256 / T;     // rows per CTA
   static constexpr int THREADS = T * ROWS;
   static constexpr int PASSES = (LOGC + 3) / 4;
-  static constexpr size_t SMEM = (size_t)ROWS * C * sizeof(u64);
+  static constexpr bool TW_TABLES = LOGC >= 8;          // sub-tree twiddles staged in shared memory
+  static constexpr size_t ROW_BYTES = (size_t)C * sizeof(u64) + (TW_TABLES ? kRowTwEntries * sizeof(Twiddle) : 0);
+  static constexpr size_t SMEM = (size_t)ROWS * ROW_BYTES;
   static constexpr int MIN_BLOCKS = THREADS <= 256 ? HEXL_B200_ROW_MIN_BLOCKS : 1;
 };
+
+// Global-memory access policies for coefficients.  Streaming (evict-first) for
+// data touched once; L2 variants for the intermediate a fused kernel hands from
+// its column phase to its row phase (written by one CTA, read by another).
+enum : int { kStream = 0, kViaL2 = 1 };
+template <int POLICY>
+__device__ __forceinline__ u64 ld_coef(const u64* p) {
+  return POLICY == kViaL2 ? __ldcg(p) : __ldcs(p);
+}
+template <int POLICY>
+__device__ __forceinline__ void st_coef(u64* p, u64 v) {
+  if (POLICY == kViaL2)
+    __stcg(p, v);
+  else
+    __stcs(p, v);
+}
+
+// Forward transform of one row of C = 2^LOGC contiguous coefficients rooted at
+// tree node `base`, by the T = C/16 threads whose index in the row is u.
+template <int MODE, int LOGC, int LD, int ST>
+__device__ __forceinline__ void row_fwd_body(u64* out, const u64* in, u64* srow, unsigned u, u64 base,
+                                             const Twiddle* __restrict__ tw, const Mod& m, int out_mf,
+                                             bool active) {
+  u64 v[16];
+  constexpr int LB0 = LOGC - 4;  // pass 0: register bits are the top 4 index bits
+  Twiddle* stab = reinterpret_cast<Twiddle*>(srow + (1 << LOGC));
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = ld_coef<LD>(in + reg_index<LB0>(u, e));
+  if constexpr (RowCfg<LOGC>::TW_TABLES) {
+    load_row_twiddles<LOGC>(stab, u, base, tw);
+    __syncthreads();
+  }
+  reg_stages<MODE, LOGC, LB0, LOGC - 1, LB0, true>(v, u, base, tw, stab, m, false, Twiddle{}, Twiddle{});
+  fwd_passes<MODE, LOGC, 1>(v, srow, u, base, tw, stab, m);
+  // registers now hold 16 consecutive coefficients per thread (LB = 0)
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = fwd_out<MODE>(v[e], m, out_mf);
+  // store layout: 16 lanes write one 128-byte line per instruction; reaching it
+  // from LB = 0 is a warp-local exchange
+  constexpr int LB_OUT = LB0 < 4 ? LB0 : 4;
+  if constexpr (LOGC > 4) smem_exchange<0, LB_OUT>(v, srow, u);
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) st_coef<ST>(out + reg_index<LB_OUT>(u, e), v[e]);
+  }
+}
+
+// Inverse transform of one row (the last log2 C ... first stages of the GS order).
+template <int MODE, int LOGC, int LD, int ST>
+__device__ __forceinline__ void row_inv_body(u64* out, const u64* in, u64* srow, unsigned u, u64 base,
+                                             const Twiddle* __restrict__ tw, const Mod& m, int out_mf,
+                                             bool fold, Twiddle inv_n, Twiddle inv_n_w, bool active) {
+  using Cfg = RowCfg<LOGC>;
+  u64 v[16];
+  constexpr int LB0 = LOGC - 4;
+  constexpr int LB_IN = LB0 < 4 ? LB0 : 4;  // 16 lanes read one 128-byte line per instruction
+  Twiddle* stab = reinterpret_cast<Twiddle*>(srow + (1 << LOGC));
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = ld_coef<LD>(in + reg_index<LB_IN>(u, e));
+  if constexpr (Cfg::TW_TABLES) {
+    load_row_twiddles<LOGC>(stab, u, base, tw);
+    __syncthreads();  // tables are filled by other warps than the ones that read them
+  }
+  // -> 16 consecutive coefficients per thread (warp-local exchange)
+  if constexpr (LOGC > 4) smem_exchange<LB_IN, 0>(v, srow, u);
+  inv_passes<MODE, LOGC, Cfg::PASSES - 1>(v, srow, u, base, tw, stab, m, fold, inv_n, inv_n_w);
+  // last pass left the registers in the coalesced layout (LB = LOGC-4);
+  // only the kernel holding the root stage applies the output range
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) st_coef<ST>(out + reg_index<LB0>(u, e), fold ? inv_out(v[e], m, out_mf) : v[e]);
+  }
+}
 
 // One CTA = ROWS rows of C contiguous coefficients.  rows_per_poly = N / C.
 template <int MODE, int LOGC>
@@ -395,27 +482,9 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS, RowCfg<LOGC>::MIN_BLOCK
   const bool active = row < total_rows;
   if (!active) row = total_rows - 1;  // keep barriers uniform; stores are masked
   const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
-  const u64* in = operand + row * Cfg::C;
-  u64* out = result + row * Cfg::C;
-  u64* srow = smem + (size_t)row_local * Cfg::C;
-
-  u64 v[16];
-  constexpr int LB0 = LOGC - 4;  // pass 0: register bits are the top 4 index bits
-#pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = __ldcs(in + reg_index<LB0>(u, e));
-  reg_stages<MODE, LOGC, LB0, LOGC - 1, LB0, true>(v, u, base, tw, m, false, Twiddle{}, Twiddle{});
-  fwd_passes<MODE, LOGC, 1>(v, srow, u, base, tw, m);
-  // registers now hold 16 consecutive coefficients per thread (LB = 0)
-#pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = fwd_out<MODE>(v[e], m, out_mf);
-  // store layout: 16 lanes write one 128-byte line per instruction; reaching it
-  // from LB = 0 is a warp-local exchange
-  constexpr int LB_OUT = LB0 < 4 ? LB0 : 4;
-  if constexpr (LOGC > 4) smem_exchange<0, LB_OUT>(v, srow, u);
-  if (active) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) __stcs(out + reg_index<LB_OUT>(u, e), v[e]);
-  }
+  row_fwd_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C,
+                                             smem + (size_t)row_local * (Cfg::ROW_BYTES / sizeof(u64)), u, base, tw, m,
+                                             out_mf, active);
 }
 
 template <int MODE, int LOGC>
@@ -430,28 +499,53 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS, RowCfg<LOGC>::MIN_BLOCK
   const bool active = row < total_rows;
   if (!active) row = total_rows - 1;
   const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
-  const u64* in = operand + row * Cfg::C;
-  u64* out = result + row * Cfg::C;
-  u64* srow = smem + (size_t)row_local * Cfg::C;
-
-  u64 v[16];
-  constexpr int LB0 = LOGC - 4;
-  constexpr int LB_IN = LB0 < 4 ? LB0 : 4;  // 16 lanes read one 128-byte line per instruction
-#pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = __ldcs(in + reg_index<LB_IN>(u, e));
-  // -> 16 consecutive coefficients per thread (warp-local exchange)
-  if constexpr (LOGC > 4) smem_exchange<LB_IN, 0>(v, srow, u);
-  inv_passes<MODE, LOGC, Cfg::PASSES - 1>(v, srow, u, base, tw, m, fold != 0, inv_n, inv_n_w);
-  // last pass left the registers in the coalesced layout (LB = LOGC-4)
-  if (active) {
-    const bool final_out = fold != 0;  // only the kernel holding the root stage reduces
-#pragma unroll
-    for (int e = 0; e < 16; ++e)
-      __stcs(out + reg_index<LB0>(u, e), final_out ? inv_out(v[e], m, out_mf) : v[e]);
-  }
+  row_inv_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C,
+                                             smem + (size_t)row_local * (Cfg::ROW_BYTES / sizeof(u64)), u, base, tw, m,
+                                             out_mf, fold != 0, inv_n, inv_n_w, active);
 }
 
 // ------------------------------------------------------------- column kernel
+// One column: R = 2^LOGR coefficients at stride 2^log_stride starting at `off`,
+// the first (forward) / last (inverse) LOGR stages of a sub-block whose R-1
+// twiddles stw[1..R-1] are laid out as a local tree (node 2^s + i).
+template <int MODE, int LOGR, bool FWD, int LD, int ST>
+__device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 off, int log_stride,
+                                         const Twiddle* stw, const Mod& m, int out_mf, bool root_fold,
+                                         Twiddle inv_n, Twiddle inv_n_w) {
+  constexpr int R = 1 << LOGR;
+  u64 v[R];
+#pragma unroll
+  for (int e = 0; e < R; ++e) v[e] = ld_coef<LD>(operand + off + ((u64)e << log_stride));
+#pragma unroll
+  for (int step = 0; step < LOGR; ++step) {
+    const int s = FWD ? step : LOGR - 1 - step;      // stage inside the sub-block
+    const int eb = LOGR - 1 - s;                     // register bit
+    const u64 cq = (!FWD && MODE == kFast) ? (u64)inv_stage_cover(step) * m.q : m.two_q;
+    if (!FWD && root_fold && s == 0) {
+#pragma unroll
+      for (int l = 0; l < (1 << eb); ++l) inv_bfly_last(v[l], v[l | (1 << eb)], inv_n, inv_n_w, m, cq);
+    } else {
+#pragma unroll
+      for (int gi = 0; gi < (1 << s); ++gi) {
+        const Twiddle w = stw[(1 << s) + gi];
+#pragma unroll
+        for (int l = 0; l < (1 << eb); ++l) {
+          const int e = (gi << (eb + 1)) | l;
+          if (FWD)
+            fwd_bfly<MODE>(v[e], v[e | (1 << eb)], w, m);
+          else
+            inv_bfly<MODE>(v[e], v[e | (1 << eb)], w, m, cq);
+        }
+      }
+    }
+  }
+  const bool final_out = !FWD && root_fold;
+  if (!FWD && MODE == kFast && !final_out) inv_pass_fixup<LOGR, R>(v, m);
+#pragma unroll
+  for (int e = 0; e < R; ++e)
+    st_coef<ST>(result + off + ((u64)e << log_stride), final_out ? inv_out(v[e], m, out_mf) : v[e]);
+}
+
 // Sub-blocks of S = 2^log_s contiguous coefficients, each rooted at tree node
 // (N/S) + block_index.  A thread owns column c of one sub-block: R coefficients
 // at stride S/R, and runs the sub-block's first log2(R) stages (forward) or last
@@ -477,39 +571,85 @@ __global__ void __launch_bounds__(256)
   const u64 g = g0 + threadIdx.x;
   if (g >= total_cols) return;
   const u64 c = g & ((1ull << log_cols) - 1);
-  const u64 off = (blk << log_s) + c;
-  const bool root = log_s == log_n;                  // this pass contains the root stage
-  u64 v[R];
-#pragma unroll
-  for (int e = 0; e < R; ++e) v[e] = __ldcs(operand + off + ((u64)e << log_cols));
-#pragma unroll
-  for (int step = 0; step < LOGR; ++step) {
-    const int s = FWD ? step : LOGR - 1 - step;      // stage inside the sub-block
-    const int eb = LOGR - 1 - s;                     // register bit
-    const u64 cq = (!FWD && MODE == kFast) ? (u64)inv_stage_cover(step) * m.q : m.two_q;
-    if (!FWD && fold && s == 0 && root) {
-#pragma unroll
-      for (int l = 0; l < (1 << eb); ++l) inv_bfly_last(v[l], v[l | (1 << eb)], inv_n, inv_n_w, m, cq);
-    } else {
-#pragma unroll
-      for (int gi = 0; gi < (1 << s); ++gi) {
-        const Twiddle w = stw[(1 << s) + gi];
-#pragma unroll
-        for (int l = 0; l < (1 << eb); ++l) {
-          const int e = (gi << (eb + 1)) | l;
-          if (FWD)
-            fwd_bfly<MODE>(v[e], v[e | (1 << eb)], w, m);
-          else
-            inv_bfly<MODE>(v[e], v[e | (1 << eb)], w, m, cq);
-        }
-      }
-    }
+  col_body<MODE, LOGR, FWD, kStream, kStream>(result, operand, (blk << log_s) + c, log_cols, stw, m, out_mf,
+                                              !FWD && fold && log_s == log_n, inv_n, inv_n_w);
+}
+
+// ------------------------------------------------------------ fused kernels
+// N = R * 4096, R = 2^LOGR in {4, 8, 16, 32}: ONE kernel per transform.  A
+// thread-block cluster of K = min(R, 8) CTAs owns one polynomial.  Forward:
+// phase 1 runs the top LOGR stages on columns (HBM -> registers -> `result`,
+// which stays in the 126 MB L2: at most ~150 clusters x 8N bytes are in flight),
+// a cluster barrier (release/acquire) publishes it, phase 2 runs the 4096-point
+// row transforms reading the intermediate back from L2.  Inverse: rows first,
+// columns second.  HBM sees each coefficient once in and once out (16N bytes),
+// half the traffic of the two-kernel path.
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int LOGR>
+struct FusedCfg {
+  static constexpr int LOGC = 12, C = 1 << LOGC, R = 1 << LOGR;
+  static constexpr int K = R < 8 ? R : 8;            // CTAs per cluster
+  static constexpr int THREADS = 256;                // = RowCfg<12>::T
+  static constexpr int MIN_BLOCKS = LOGR <= 4 ? HEXL_B200_ROW_MIN_BLOCKS : 2;
+  static constexpr size_t SMEM = RowCfg<LOGC>::ROW_BYTES;
+};
+
+template <int MODE, int LOGR>
+__global__ void __launch_bounds__(FusedCfg<LOGR>::THREADS, FusedCfg<LOGR>::MIN_BLOCKS)
+    ntt_fused_fwd(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m, int out_mf) {
+  using Cfg = FusedCfg<LOGR>;
+  extern __shared__ __align__(16) u64 smem[];
+  __shared__ Twiddle stw[Cfg::R];
+  const unsigned rank = blockIdx.x % Cfg::K;         // == %cluster_ctarank (1-D clusters)
+  const u64 poly_off = (u64)(blockIdx.x / Cfg::K) << (Cfg::LOGC + LOGR);
+  for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
+    if (l) stw[l] = ld_tw(tw + l);                   // root sub-tree: local node == global node
+  __syncthreads();
+  // phase 1: columns rank*C/K ... of this polynomial
+  constexpr int COLS = Cfg::C / Cfg::K;
+#pragma unroll 1
+  for (int c = threadIdx.x; c < COLS; c += Cfg::THREADS)
+    col_body<MODE, LOGR, true, kStream, kViaL2>(result, operand, poly_off + rank * COLS + c, Cfg::LOGC, stw, m,
+                                                out_mf, false, Twiddle{}, Twiddle{});
+  cluster_barrier();
+  // phase 2: rows rank, rank+K, ...
+#pragma unroll 1
+  for (unsigned r = rank; r < Cfg::R; r += Cfg::K) {
+    u64* row = result + poly_off + (u64)r * Cfg::C;
+    row_fwd_body<MODE, Cfg::LOGC, kViaL2, kStream>(row, row, smem, threadIdx.x, (u64)Cfg::R + r, tw, m, out_mf, true);
+    if (r + Cfg::K < Cfg::R) __syncthreads();       // the next row reuses the shared buffer
   }
-  const bool final_out = !FWD && fold && root;
-  if (!FWD && MODE == kFast && !final_out) inv_pass_fixup<LOGR, R>(v, m);
-#pragma unroll
-  for (int e = 0; e < R; ++e)
-    __stcs(result + off + ((u64)e << log_cols), final_out ? inv_out(v[e], m, out_mf) : v[e]);
+}
+
+template <int MODE, int LOGR>
+__global__ void __launch_bounds__(FusedCfg<LOGR>::THREADS, FusedCfg<LOGR>::MIN_BLOCKS)
+    ntt_fused_inv(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m, int out_mf,
+                  Twiddle inv_n, Twiddle inv_n_w) {
+  using Cfg = FusedCfg<LOGR>;
+  extern __shared__ __align__(16) u64 smem[];
+  __shared__ Twiddle stw[Cfg::R];
+  const unsigned rank = blockIdx.x % Cfg::K;
+  const u64 poly_off = (u64)(blockIdx.x / Cfg::K) << (Cfg::LOGC + LOGR);
+  for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
+    if (l) stw[l] = ld_tw(tw + l);
+  // phase 1: rows (the __syncthreads inside/after each row also publishes stw)
+#pragma unroll 1
+  for (unsigned r = rank; r < Cfg::R; r += Cfg::K) {
+    const u64 off = poly_off + (u64)r * Cfg::C;
+    row_inv_body<MODE, Cfg::LOGC, kStream, kViaL2>(result + off, operand + off, smem, threadIdx.x, (u64)Cfg::R + r,
+                                                   tw, m, out_mf, false, inv_n, inv_n_w, true);
+    __syncthreads();
+  }
+  cluster_barrier();
+  // phase 2: columns, root stage folded with N^-1
+  constexpr int COLS = Cfg::C / Cfg::K;
+#pragma unroll 1
+  for (int c = threadIdx.x; c < COLS; c += Cfg::THREADS)
+    col_body<MODE, LOGR, false, kViaL2, kStream>(result, result, poly_off + rank * COLS + c, Cfg::LOGC, stw, m,
+                                                 out_mf, true, inv_n, inv_n_w);
 }
 
 // --------------------------------------------------------- tiny-N stage kernel
@@ -691,9 +831,55 @@ cudaError_t simple_transform(bool fwd, const NttDeviceTables& t, u64* result, co
   return cudaGetLastError();
 }
 
+template <int MODE, int LOGR>
+cudaError_t launch_fused(bool fwd, const NttDeviceTables& t, u64* result, const u64* operand, u64 batch,
+                         int out_mf, cudaStream_t stream) {
+  using Cfg = FusedCfg<LOGR>;
+  const Mod m = make_mod(t);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(batch * Cfg::K));
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = Cfg::K;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (fwd)
+    e = cudaLaunchKernelEx(&cfg, ntt_fused_fwd<MODE, LOGR>, result, operand, t.fwd, m, out_mf);
+  else
+    e = cudaLaunchKernelEx(&cfg, ntt_fused_inv<MODE, LOGR>, result, operand, t.inv, m, out_mf, t.inv_n, t.inv_n_w);
+  count_launch();
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// log2(N / 4096) for which the single fused kernel is used; 0 = none
+int fused_log_r(int log_n) {
+  static const bool enabled = env_int("HEXL_B200_FUSED", 1) != 0;
+  const int lr = log_n - FusedCfg<2>::LOGC;
+  return (enabled && lr >= 2 && lr <= 5) ? lr : 0;
+}
+
+template <int MODE>
+cudaError_t launch_fused_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64* result, const u64* operand,
+                             u64 batch, int out_mf, cudaStream_t stream) {
+  switch (log_r) {
+    case 2: return launch_fused<MODE, 2>(fwd, t, result, operand, batch, out_mf, stream);
+    case 3: return launch_fused<MODE, 3>(fwd, t, result, operand, batch, out_mf, stream);
+    case 4: return launch_fused<MODE, 4>(fwd, t, result, operand, batch, out_mf, stream);
+    case 5: return launch_fused<MODE, 5>(fwd, t, result, operand, batch, out_mf, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
 template <int MODE>
 cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
+  if (const int lr = fused_log_r(t.log_n)) return launch_fused_dyn<MODE>(lr, true, t, result, operand, batch, out_mf, stream);
   const int log_c = pick_row_log(t.log_n);
   int radices[8];
   const int ncol = plan_col_passes(t.log_n - log_c, radices);
@@ -711,6 +897,7 @@ cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* opera
 template <int MODE>
 cudaError_t inverse_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
+  if (const int lr = fused_log_r(t.log_n)) return launch_fused_dyn<MODE>(lr, false, t, result, operand, batch, out_mf, stream);
   const int log_c = pick_row_log(t.log_n);
   int radices[8];
   const int ncol = plan_col_passes(t.log_n - log_c, radices);
