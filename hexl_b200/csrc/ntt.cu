@@ -859,7 +859,7 @@ cudaError_t launch_fused(bool fwd, const NttDeviceTables& t, u64* result, const 
 
 // log2(N / 4096) for which the single fused kernel is used; 0 = none
 int fused_log_r(int log_n) {
-  static const bool enabled = env_int("HEXL_B200_FUSED", 1) != 0;
+  static const bool enabled = env_int("HEXL_B200_FUSED", 0) != 0;
   const int lr = log_n - FusedCfg<2>::LOGC;
   return (enabled && lr >= 2 && lr <= 5) ? lr : 0;
 }

@@ -121,6 +121,25 @@ __device__ __forceinline__ void bf8(u64& X, u64& Y, Tw w, const Mod& m) {
   Y = X + m.four_q - T; X = X + T;
 }
 
+// ---- variant 9: quotient cross terms on the FP64 pipe.
+//   Q ~ a1*p1 + K,  K = round(a1*(p0/2^32) + a0*(p1/2^32) - 1)  in {floor-1, floor}
+//   (w.wp reinterpreted: here b0s/b1s are derived on the fly from wp only to keep the
+//   benchmark self-contained; a real table would store them)
+struct TwD { u64 w; double b0s, b1s; unsigned p1; };
+__device__ __forceinline__ double u32_to_double(unsigned a) {
+  // bit pattern of 2^52 + a, then remove 2^52 exactly
+  return __hiloint2double(0x43300000, (int)a) - 4503599627370496.0;
+}
+__device__ __forceinline__ void bf9(u64& X, u64& Y, const TwD& w, const Mod& m) {
+  unsigned y0, y1; split(Y, y0, y1);
+  const double d = fma(u32_to_double(y0), w.b1s, u32_to_double(y1) * w.b0s);   // (a1*p0 + a0*p1) / 2^32
+  const double mg = d + 4503599627370495.0;                                      // 2^52 - 1 + d -> integer in the mantissa
+  u64 K = (u64)__double_as_longlong(mg) - 0x4330000000000000ull;
+  u64 Q = madwide(y1, w.p1, K);
+  u64 T = mad_chain5(Y, w.w, Q, m);
+  Y = X + m.four_q - T; X = X + T;
+}
+
 template <int V> __device__ __forceinline__ void bf(u64& X, u64& Y, Tw w, const Mod& m) {
   if (V == 5) { bf5(X, Y, w, m); return; } if (V == 6) { bf6(X, Y, w, m); return; }
   if (V == 7) { bf7(X, Y, w, m); return; } if (V == 8) { bf8(X, Y, w, m); return; }
@@ -158,6 +177,57 @@ __global__ void __launch_bounds__(256, MINB) kern(u64* out, const Tw* tw, Mod m,
   out[tid] = acc;
 }
 
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) kern9(u64* out, const Tw* tw, Mod m, int iters) {
+  u64 v[16];
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = (u64)tid * 0x9E3779B97F4A7C15ull + e * 0x1234567ull;
+  TwD w[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    Tw t = tw[(tid + g) & 1023];
+    w[g].w = t.w; w[g].p1 = hi32(t.wp);
+    w[g].b0s = (double)lo32(t.wp) * (1.0 / 4294967296.0); w[g].b1s = (double)hi32(t.wp) * (1.0 / 4294967296.0);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int g = 0; g < 1; ++g)
+#pragma unroll
+      for (int l = 0; l < 8; ++l) bf9(v[l], v[l | 8], w[0], m);
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) bf9(v[(g << 3) | l], v[((g << 3) | l) | 4], w[g], m);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int l = 0; l < 2; ++l) bf9(v[(g << 2) | l], v[((g << 2) | l) | 2], w[g], m);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) bf9(v[g << 1], v[(g << 1) | 1], w[g], m);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] &= (1ull << 60) - 1;
+  }
+  u64 acc = 0;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc ^= v[e];
+  out[tid] = acc;
+}
+template <int MINB> void run9(const char* name, u64* out, const Tw* tw, Mod m, int blocks_per_sm) {
+  const int iters = 2000, grid = 148 * blocks_per_sm;
+  kern9<MINB><<<grid, 256>>>(out, tw, m, 10);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a);
+  kern9<MINB><<<grid, 256>>>(out, tw, m, iters);
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  double bfl = (double)grid * 256 * iters * 32;
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern9<MINB>);
+  printf("%-28s blocks/SM %d regs %3d : %8.1f G bfly/s = %6.3f M NTT(2^16)/s = %5.1f SMSP-cycles per warp-bfly  %s\n", name,
+         blocks_per_sm, fa.numRegs, bfl / ms / 1e6, bfl / ms / 1e6 / 524288.0 * 1e3, 592.0 * 1.965e9 / (bfl / ms * 1e3 / 32),
+         cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int V, int MINB> void run(const char* name, u64* out, const Tw* tw, Mod m, int blocks_per_sm) {
   const int iters = 2000, grid = 148 * blocks_per_sm;
   kern<V, MINB><<<grid, 256>>>(out, tw, m, 10);
@@ -189,6 +259,9 @@ int main() {
     run<7, 2>("v7 multiplies only", out, tw, m, bps);
     run<8, 2>("v8 adds only", out, tw, m, bps);
   }
+  run9<2>("v9 fp64 cross terms", out, tw, m, 2);
+  run9<2>("v9 fp64 cross terms", out, tw, m, 3);
+  run9<3>("v9 mb3", out, tw, m, 3);
   run<5, 3>("v5 mb3", out, tw, m, 3);
   run<6, 3>("v6 mb3", out, tw, m, 3);
   run<7, 3>("v7 mb3", out, tw, m, 3);

@@ -15,7 +15,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag, launches, rep = sys.argv[1:4]
+tag, launches = sys.argv[1:3]
+reps = sys.argv[3:]
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
@@ -49,8 +50,17 @@ with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
         f.write(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1e6:.3f} | {share} |\n")
 
 # ---- full capture
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
+rows = []
+for rep in reps:
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    part = list(csv.reader(raw.splitlines()))
+    if not rows:
+        rows = part
+    else:  # align columns by name
+        Hp = part[0]
+        for r in part[2:]:
+            d = dict(zip(Hp, r))
+            rows.append([d.get(h, "") for h in rows[0]])
 H, U = rows[0], rows[1]
 want = [
     ("gpu__time_duration.sum", "duration"),
