@@ -100,6 +100,10 @@ _sig("hexl_b200_eltwise_reduce_mod", _int, [_vp, _vp, _u64, _u64, _u64, _u64, _v
 _sig("hexl_b200_eltwise_cmp_add", _int, [_vp, _vp, _u64, _int, _u64, _u64, _vp])
 _sig("hexl_b200_eltwise_cmp_sub_mod", _int, [_vp, _vp, _u64, _u64, _int, _u64, _u64, _vp])
 
+_sig("hexl_b200_ntt_get_cached", _int, [C.POINTER(_vp), _u64, _u64])
+_sig("hexl_b200_dyadic_multiply", _int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp])
+_sig("hexl_b200_key_switch", _int, [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp, _vp, _vp])
+
 #: every symbol include/hexl_b200.h declares (checked against the header by the tests)
 EXPORTED = sorted(n for n in dir(_lib) if n.startswith("hexl_b200_"))
 
@@ -300,4 +304,36 @@ def EltwiseCmpSubMod(result, operand1, n, modulus, cmp, bound, diff, stream=None
     rp, _, rc = _buf(result); ap, _, ac = _buf(operand1)
     _check(_lib.hexl_b200_eltwise_cmp_sub_mod(rp, ap, n, modulus, int(cmp), bound, diff,
                                               _stream(stream, rc or ac)))
+    return result
+
+
+# ------------------------------------------------------- SEAL-shaped composites
+def GetNTT(N: int, modulus: int) -> NTT:
+    """hexl/include/hexl/experimental/seal/ntt-cache.hpp:27-53: process-wide cache"""
+    h = _vp()
+    _check(_lib.hexl_b200_ntt_get_cached(C.byref(h), N, modulus))
+    obj = NTT.__new__(NTT)
+    obj._h = h
+    return obj
+
+
+def DyadicMultiply(result, operand1, operand2, n, moduli, num_moduli=None, stream=None):
+    """hexl/include/hexl/experimental/seal/dyadic-multiply.hpp:26"""
+    mods = np.ascontiguousarray(moduli, dtype=np.uint64)
+    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1); bp, _, _ = _buf(operand2)
+    _check(_lib.hexl_b200_dyadic_multiply(rp, ap, bp, n, mods.ctypes.data, num_moduli or mods.size,
+                                          _stream(stream, rc or ac)))
+    return result
+
+
+def KeySwitch(result, t_target_iter_ptr, n, decomp_modulus_size, key_modulus_size, rns_modulus_size,
+              key_component_count, moduli, k_switch_keys, modswitch_factors, stream=None):
+    """hexl/include/hexl/experimental/seal/key-switch.hpp:34; k_switch_keys is a list of buffers"""
+    mods = np.ascontiguousarray(moduli, dtype=np.uint64)
+    ms = np.ascontiguousarray(modswitch_factors, dtype=np.uint64)
+    rp, _, rc = _buf(result); tp, _, tc = _buf(t_target_iter_ptr)
+    key_ptrs = (_vp * len(k_switch_keys))(*[_buf(k)[0] for k in k_switch_keys])
+    _check(_lib.hexl_b200_key_switch(rp, tp, n, decomp_modulus_size, key_modulus_size, rns_modulus_size,
+                                     key_component_count, mods.ctypes.data, key_ptrs, ms.ctypes.data,
+                                     _stream(stream, rc or tc)))
     return result

@@ -25,7 +25,7 @@ OBJ = os.path.join(PKG, "_obj" + SUFFIX)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, f"libhexl_b200{SUFFIX}.so")
 
-SOURCES = ["capi.cu", "ntt.cu", "eltwise.cu", "numtheory.cpp"]
+SOURCES = ["capi.cu", "ntt.cu", "eltwise.cu", "seal.cu", "numtheory.cpp"]
 HEADERS = ["internal.h", "modarith.cuh", "numtheory.h", os.path.join(ROOT, "include", "hexl_b200.h")]
 
 NVCC_FLAGS = [

@@ -477,6 +477,143 @@ int eltwise_dispatch(EltOp op, EltParams p, void* stream) {
 #define REQUIRE(cond, ...) \
   if (!(cond)) return fail(HEXL_B200_ERR_INVALID_ARG, __VA_ARGS__)
 
+// ------------------------------------------------------------ NTT cache
+// GetNTT(N, modulus) of the reference (hexl/include/hexl/experimental/seal/ntt-cache.hpp:27-53)
+std::mutex g_cache_mu;
+std::map<std::pair<uint64_t, uint64_t>, hexl_b200_ntt*> g_ntt_cache;
+
+int cached_ntt(hexl_b200_ntt** out, uint64_t n, uint64_t q) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  auto key = std::make_pair(n, q);
+  auto it = g_ntt_cache.find(key);
+  if (it == g_ntt_cache.end()) {
+    hexl_b200_ntt* h = nullptr;
+    if (int rc = create_common(&h, n, q, 0, false)) return rc;
+    it = g_ntt_cache.emplace(key, h).first;  // the cache keeps its own reference for the process lifetime
+  }
+  it->second->refs.fetch_add(1);
+  *out = it->second;
+  return 0;
+}
+
+// stream-ordered scratch memory for the composites
+struct Scratch {
+  cudaStream_t s;
+  std::vector<void*> ptrs;
+  explicit Scratch(cudaStream_t st) : s(st) {}
+  template <class T>
+  int get(T** p, size_t count) {
+    void* v = nullptr;
+    CU(cudaMallocAsync(&v, count * sizeof(T) + 16, s));
+    ptrs.push_back(v);
+    *p = static_cast<T*>(v);
+    return 0;
+  }
+  ~Scratch() {
+    for (void* v : ptrs) cudaFreeAsync(v, s);
+  }
+};
+
+DyadicModulus dyadic_modulus(uint64_t q) {
+  const int L = floor_log2(q) + 1;
+  return DyadicModulus{q, nt::multiply_factor(1ull << (L - 2), 64, q), L - 2};
+}
+
+int dyadic_on_device(uint64_t* result, const uint64_t* op1, const uint64_t* op2, uint64_t n, const uint64_t* moduli,
+                     uint64_t num_moduli, cudaStream_t s) {
+  std::vector<DyadicModulus> mods(num_moduli);
+  for (uint64_t i = 0; i < num_moduli; ++i) mods[i] = dyadic_modulus(moduli[i]);
+  Scratch ws(s);
+  DyadicModulus* d_mods = nullptr;
+  if (int rc = ws.get(&d_mods, num_moduli)) return rc;
+  CU(cudaMemcpyAsync(d_mods, mods.data(), num_moduli * sizeof(DyadicModulus), cudaMemcpyHostToDevice, s));
+  cudaError_t e = launch_dyadic_multiply(result, op1, op2, n, num_moduli, d_mods, s);
+  if (e != cudaSuccess) return cuda_fail(e, "DyadicMultiply launch");
+  CU(cudaStreamSynchronize(s));  // `mods` is pageable host memory feeding an async copy
+  return 0;
+}
+
+// key-switch-internal.cpp:25-201 as a stream-ordered chain of kernels; every
+// pointer is a device pointer on the current device.
+int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, uint64_t n, uint64_t decomp,
+                         uint64_t key_modulus_size, uint64_t rns, uint64_t kcc, const uint64_t* moduli,
+                         const uint64_t* const* d_key_ptrs_host, const uint64_t* modswitch, cudaStream_t s) {
+  std::vector<hexl_b200_ntt*> h(key_modulus_size, nullptr);
+  std::vector<NttDeviceTables> tab(key_modulus_size);
+  struct Release {
+    std::vector<hexl_b200_ntt*>& v;
+    ~Release() {
+      for (auto* p : v)
+        if (p) hexl_b200_ntt_release(p);
+    }
+  } release{h};
+  for (uint64_t i = 0; i < key_modulus_size; ++i) {
+    if (int rc = cached_ntt(&h[i], n, moduli[i])) return rc;
+    if (int rc = device_tables(h[i], dev, &tab[i])) return rc;
+  }
+  Scratch ws(s);
+  uint64_t *t_coef = nullptr, *ops = nullptr, *prod = nullptr, *tmp = nullptr;
+  const uint64_t** d_keys = nullptr;
+  if (int rc = ws.get(&t_coef, decomp * n)) return rc;
+  if (int rc = ws.get(&ops, decomp * n)) return rc;
+  if (int rc = ws.get(&prod, kcc * rns * n)) return rc;
+  if (int rc = ws.get(&tmp, decomp * kcc * n)) return rc;
+  if (int rc = ws.get(&d_keys, decomp)) return rc;
+  CU(cudaMemcpyAsync(d_keys, d_key_ptrs_host, decomp * sizeof(uint64_t*), cudaMemcpyHostToDevice, s));
+#define LAUNCH(expr)                                                    \
+  do {                                                                  \
+    cudaError_t e__ = (expr);                                           \
+    if (e__ != cudaSuccess) return cuda_fail(e__, "KeySwitch: " #expr); \
+  } while (0)
+  // 1. digits back to coefficient form (:49-55)
+  for (uint64_t j = 0; j < decomp; ++j)
+    LAUNCH(launch_ntt_inverse(tab[j], t_coef + j * n, t_target + j * n, 2, 1, 1, s));
+  // 2. per RNS modulus: convert every other digit, multiply-accumulate with the keys (:60-131)
+  for (uint64_t i = 0; i < rns; ++i) {
+    const uint64_t ki = (i == decomp) ? key_modulus_size - 1 : i;
+    const uint64_t q = moduli[ki], mu = nt::multiply_factor(1, 64, q);
+    // x mod q for every digit: the reference copies when q_j <= q (then x < q already) and
+    // reduces otherwise (:77-85); one Barrett pass over all digits does both
+    EltParams rp{};
+    rp.result = ops; rp.a = t_coef; rp.n = decomp * n; rp.q = q; rp.mu = mu; rp.in_mf = 0; rp.out_mf = 1;
+    LAUNCH(launch_eltwise(EltOp::Reduce, rp, s));
+    if (i > 0 || i == decomp) {
+      const uint64_t cnt = (i < decomp) ? i : decomp;
+      if (cnt) LAUNCH(launch_ntt_forward(tab[ki], ops, ops, 4, 4, cnt, s));
+    }
+    if (i < decomp) {
+      if (i + 1 < decomp)
+        LAUNCH(launch_ntt_forward(tab[ki], ops + (i + 1) * n, ops + (i + 1) * n, 4, 4, decomp - i - 1, s));
+      CU(cudaMemcpyAsync(ops + i * n, t_target + i * n, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
+    }
+    const uint64_t r64 = nt::multiply_factor(1, 64, q) * (0 - q) /* 2^64 - floor(2^64/q)*q = 2^64 mod q */;
+    const Twiddle R = make_twiddle(r64 % q, q);
+    LAUNCH(launch_ks_mac(prod + i * n, ops, d_keys, n, decomp, kcc, ki, key_modulus_size, rns * n, q, mu, R, s));
+  }
+  // 3. mod-down by the special prime and accumulate into result (:134-198)
+  const uint64_t q_last = moduli[key_modulus_size - 1], mu_last = nt::multiply_factor(1, 64, q_last);
+  for (uint64_t k = 0; k < kcc; ++k) {
+    uint64_t* t_last = prod + k * rns * n + decomp * n;
+    LAUNCH(launch_ntt_inverse(tab[key_modulus_size - 1], t_last, t_last, 2, 2, 1, s));
+    for (uint64_t i = 0; i < decomp; ++i) {
+      const uint64_t qi = moduli[i], mu_i = nt::multiply_factor(1, 64, qi);
+      const uint64_t fix = qi - ((q_last >> 1) % qi);
+      LAUNCH(launch_ks_round(tmp + (i * kcc + k) * n, t_last, n, q_last, mu_last, qi, mu_i, fix, s));
+    }
+  }
+  for (uint64_t i = 0; i < decomp; ++i) {
+    const uint64_t qi = moduli[i];
+    LAUNCH(launch_ntt_forward(tab[i], tmp + i * kcc * n, tmp + i * kcc * n, 4, 4, kcc, s));
+    const Twiddle ms = make_twiddle(modswitch[i] % qi, qi);
+    for (uint64_t k = 0; k < kcc; ++k)
+      LAUNCH(launch_ks_finish(result + n * (decomp * k + i), prod + k * rns * n + i * n, tmp + (i * kcc + k) * n, n, qi,
+                              ms.w, ms.wp, s));
+  }
+#undef LAUNCH
+  CU(cudaStreamSynchronize(s));  // scratch and the pointer table are released by ~Scratch after this
+  return 0;
+}
+
 int debug_bounds(const u64* p, u64 n, u64 bound, const char* what, std::initializer_list<const void*> all) {
   if (!g_debug.load()) return 0;
   PtrInfo pi;
@@ -751,6 +888,88 @@ int hexl_b200_eltwise_cmp_sub_mod(uint64_t* result, const uint64_t* op1, uint64_
   p.result = result; p.a = op1; p.n = n; p.q = q; p.scalar = bound; p.scalar_p = diff; p.cmp = cmp;
   p.mu = nt::multiply_factor(1, 64, q);
   return eltwise_dispatch(EltOp::CmpSubMod, p, stream);
+}
+
+// ---- SEAL-shaped composites
+int hexl_b200_ntt_get_cached(hexl_b200_ntt** out, uint64_t degree, uint64_t q) {
+  if (!out) return fail(HEXL_B200_ERR_INVALID_ARG, "out == nullptr");
+  return cached_ntt(out, degree, q);
+}
+
+int hexl_b200_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2, uint64_t n,
+                              const uint64_t* moduli, uint64_t num_moduli, void* stream) {
+  // dyadic-multiply-internal.cpp:20-24
+  REQUIRE(result && operand1 && operand2 && moduli, "Require result, operand1, operand2, moduli != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(num_moduli != 0, "Require num_moduli != 0");
+  for (uint64_t i = 0; i < num_moduli; ++i)
+    REQUIRE(moduli[i] > 1 && moduli[i] < (1ull << 62), "Require 1 < modulus < 2^62");
+  PtrInfo pi;
+  if (int rc = classify_all({result, operand1, operand2}, &pi)) return rc;
+  const size_t in_elems = 2 * n * num_moduli, out_elems = 3 * n * num_moduli;
+  if (pi.where == Where::Device) {
+    DeviceGuard g;
+    if (int rc = g.enter(pi.device)) return rc;
+    return dyadic_on_device(result, operand1, operand2, n, moduli, num_moduli, (cudaStream_t)stream);
+  }
+  int cur = 0;
+  CU(cudaGetDevice(&cur));
+  Scratch ws(nullptr);
+  uint64_t *d1 = nullptr, *d2 = nullptr, *dr = nullptr;
+  if (int rc = ws.get(&d1, in_elems)) return rc;
+  if (int rc = ws.get(&d2, in_elems)) return rc;
+  if (int rc = ws.get(&dr, out_elems)) return rc;
+  CU(cudaMemcpyAsync(d1, operand1, in_elems * 8, cudaMemcpyHostToDevice, nullptr));
+  CU(cudaMemcpyAsync(d2, operand2, in_elems * 8, cudaMemcpyHostToDevice, nullptr));
+  if (int rc = dyadic_on_device(dr, d1, d2, n, moduli, num_moduli, nullptr)) return rc;
+  CU(cudaMemcpy(result, dr, out_elems * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int hexl_b200_key_switch(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n, uint64_t decomp,
+                         uint64_t key_modulus_size, uint64_t rns, uint64_t kcc, const uint64_t* moduli,
+                         const uint64_t* const* k_switch_keys, const uint64_t* modswitch_factors, void* stream) {
+  REQUIRE(result && t_target_iter_ptr && moduli && k_switch_keys && modswitch_factors, "Require non-null arguments");
+  REQUIRE(n >= 2 && !(n & (n - 1)), "Require n a power of two");
+  REQUIRE(decomp >= 1 && kcc >= 1, "Require decomp_modulus_size, key_component_count >= 1");
+  REQUIRE(rns == decomp + 1, "Require rns_modulus_size == decomp_modulus_size + 1");
+  REQUIRE(key_modulus_size >= rns, "Require key_modulus_size >= rns_modulus_size");
+  for (uint64_t j = 0; j < decomp; ++j) REQUIRE(k_switch_keys[j] != nullptr, "Require k_switch_keys[j] != nullptr");
+  PtrInfo pi;
+  if (int rc = classify_all({result, t_target_iter_ptr}, &pi)) return rc;
+  for (uint64_t j = 0; j < decomp; ++j) {
+    PtrInfo pk;
+    if (int rc = classify(k_switch_keys[j], &pk)) return rc;
+    if (pk.where != pi.where || (pk.where == Where::Device && pk.device != pi.device))
+      return fail(HEXL_B200_ERR_MIXED_POINTERS, "k_switch_keys[%llu] lives elsewhere than result", (unsigned long long)j);
+  }
+  if (pi.where == Where::Device) {
+    DeviceGuard g;
+    if (int rc = g.enter(pi.device)) return rc;
+    return key_switch_on_device(pi.device, result, t_target_iter_ptr, n, decomp, key_modulus_size, rns, kcc, moduli,
+                                k_switch_keys, modswitch_factors, (cudaStream_t)stream);
+  }
+  int cur = 0;
+  CU(cudaGetDevice(&cur));
+  Scratch ws(nullptr);
+  const size_t res_elems = kcc * decomp * n, key_elems = kcc * key_modulus_size * n;
+  uint64_t *d_res = nullptr, *d_t = nullptr;
+  if (int rc = ws.get(&d_res, res_elems)) return rc;
+  if (int rc = ws.get(&d_t, decomp * n)) return rc;
+  std::vector<const uint64_t*> d_keys(decomp);
+  for (uint64_t j = 0; j < decomp; ++j) {
+    uint64_t* dk = nullptr;
+    if (int rc = ws.get(&dk, key_elems)) return rc;
+    CU(cudaMemcpyAsync(dk, k_switch_keys[j], key_elems * 8, cudaMemcpyHostToDevice, nullptr));
+    d_keys[j] = dk;
+  }
+  CU(cudaMemcpyAsync(d_res, result, res_elems * 8, cudaMemcpyHostToDevice, nullptr));
+  CU(cudaMemcpyAsync(d_t, t_target_iter_ptr, decomp * n * 8, cudaMemcpyHostToDevice, nullptr));
+  if (int rc = key_switch_on_device(cur, d_res, d_t, n, decomp, key_modulus_size, rns, kcc, moduli, d_keys.data(),
+                                    modswitch_factors, nullptr))
+    return rc;
+  CU(cudaMemcpy(result, d_res, res_elems * 8, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 }  // extern "C"

@@ -54,6 +54,21 @@ cudaError_t launch_ntt_forward(const NttDeviceTables& t, u64* result, const u64*
 cudaError_t launch_ntt_inverse(const NttDeviceTables& t, u64* result, const u64* operand,
                                int in_mf, int out_mf, u64 batch, cudaStream_t stream);
 
+// ----------------------------------------------------- SEAL-shaped composites
+struct DyadicModulus {  // per RNS modulus: q and its generalised-Barrett constants
+  u64 q, mu;
+  int shift;
+};
+cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli,
+                                   const DyadicModulus* d_mods, cudaStream_t stream);
+cudaError_t launch_ks_mac(u64* prod_i, const u64* operands, const u64* const* d_keys, u64 n, u64 decomp, u64 kcc,
+                          u64 key_index, u64 key_modulus_size, u64 prod_stride_k, u64 q, u64 mu, Twiddle r64,
+                          cudaStream_t stream);
+cudaError_t launch_ks_round(u64* out, const u64* t_last, u64 n, u64 q_last, u64 mu_last, u64 q_i, u64 mu_i, u64 fix,
+                            cudaStream_t stream);
+cudaError_t launch_ks_finish(u64* result, const u64* prod, const u64* t_ntt, u64 n, u64 q, u64 ms, u64 ms_p,
+                             cudaStream_t stream);
+
 // launches issued so far (all kernels of this library)
 void count_launch(unsigned n = 1);
 uint64_t launches_so_far();

@@ -364,6 +364,13 @@ class NTT {
 
   // extension: the underlying C handle (e.g. to pass across an FFI)
   hexl_b200_ntt* Handle() const { return m_handle; }
+  // extension: the process-wide cached object for (N, modulus) -- GetNTT below
+  static NTT FromCache(uint64_t degree, uint64_t q) {
+    NTT t;
+    b200_detail::Throw(hexl_b200_ntt_get_cached(&t.m_handle, degree, q));
+    t.InitTables();
+    return t;
+  }
 
  private:
   using Vec = AlignedVector64<uint64_t>;
@@ -471,6 +478,30 @@ inline void EltwiseCmpSubMod(uint64_t* result, const uint64_t* operand1, uint64_
                              uint64_t bound, uint64_t diff, void* stream = nullptr) {
   b200_detail::Throw(
       hexl_b200_eltwise_cmp_sub_mod(result, operand1, n, modulus, static_cast<int>(cmp), bound, diff, stream));
+}
+
+// ------------------------------------------------ SEAL-shaped composites
+// hexl/include/hexl/experimental/seal/ntt-cache.hpp:27-53.  The reference returns
+// NTT& into a process-wide map; here the cache lives behind the ABI and a cheap
+// handle copy is returned.
+inline NTT GetNTT(size_t N, uint64_t modulus) { return NTT::FromCache(N, modulus); }
+
+// hexl/include/hexl/experimental/seal/dyadic-multiply.hpp:26
+inline void DyadicMultiply(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2, uint64_t n,
+                           const uint64_t* moduli, uint64_t num_moduli, void* stream = nullptr) {
+  b200_detail::Throw(hexl_b200_dyadic_multiply(result, operand1, operand2, n, moduli, num_moduli, stream));
+}
+
+// hexl/include/hexl/experimental/seal/key-switch.hpp:34
+inline void KeySwitch(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n, uint64_t decomp_modulus_size,
+                      uint64_t key_modulus_size, uint64_t rns_modulus_size, uint64_t key_component_count,
+                      const uint64_t* moduli, const uint64_t** k_switch_keys, const uint64_t* modswitch_factors,
+                      const uint64_t* root_of_unity_powers_ptr = nullptr, void* stream = nullptr) {
+  if (root_of_unity_powers_ptr != nullptr)  // key-switch-internal.cpp:31-34
+    throw std::invalid_argument("Parameter root_of_unity_powers_ptr is not supported yet.");
+  b200_detail::Throw(hexl_b200_key_switch(result, t_target_iter_ptr, n, decomp_modulus_size, key_modulus_size,
+                                          rns_modulus_size, key_component_count, moduli, k_switch_keys,
+                                          modswitch_factors, stream));
 }
 
 }  // namespace hexl

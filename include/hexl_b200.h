@@ -156,6 +156,26 @@ int hexl_b200_eltwise_cmp_sub_mod(uint64_t* result, const uint64_t* operand1, ui
                                   uint64_t modulus, int cmp, uint64_t bound, uint64_t diff,
                                   void* stream);
 
+/* ---- SEAL-shaped composites built on the hot path (hexl/include/hexl/experimental/seal/)
+ * `moduli`, `modswitch_factors` and the array `k_switch_keys` itself are small HOST
+ * arrays; the coefficient buffers (result, operands, t_target, every k_switch_keys[j])
+ * are all device pointers or all host pointers. */
+/* NTT cache, GetNTT(N, modulus): ntt-cache.hpp:27-53.  Returns a retained handle
+ * shared by every caller; release it with hexl_b200_ntt_release. */
+int hexl_b200_ntt_get_cached(hexl_b200_ntt** out, uint64_t degree, uint64_t q);
+/* DyadicMultiply, dyadic-multiply.hpp:26: (x0*y0, x0*y1 + x1*y0, x1*y1) per modulus;
+ * operands hold 2 polynomials x num_moduli x n, result 3; result may alias an operand. */
+int hexl_b200_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                              uint64_t n, const uint64_t* moduli, uint64_t num_moduli, void* stream);
+/* KeySwitch, key-switch.hpp:34 (CKKS): result (key_component_count x decomp x n) is
+ * updated in place; t_target_iter_ptr holds decomp x n digits in NTT form;
+ * k_switch_keys[j] holds key_component_count x key_modulus_size x n. */
+int hexl_b200_key_switch(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n,
+                         uint64_t decomp_modulus_size, uint64_t key_modulus_size, uint64_t rns_modulus_size,
+                         uint64_t key_component_count, const uint64_t* moduli,
+                         const uint64_t* const* k_switch_keys, const uint64_t* modswitch_factors,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,6 +92,8 @@ class Port:
         L.orc_eltwise_reduce_mod.argtypes = [vp, vp, u64, u64, u64, u64]
         L.orc_eltwise_cmp_add.argtypes = [vp, vp, u64, C.c_int, u64, u64]
         L.orc_eltwise_cmp_sub_mod.argtypes = [vp, vp, u64, u64, C.c_int, u64, u64]
+        L.orc_dyadic_multiply.argtypes = [vp, vp, vp, u64, vp, u64]
+        L.orc_key_switch.argtypes = [vp, vp, u64, u64, u64, u64, u64, vp, vp, vp]
         self._tables = {}
 
     # -- number theory
@@ -193,6 +195,34 @@ class Port:
         self.L.orc_eltwise_cmp_sub_mod(_ptr(r), _ptr(a), a.size, q, int(cmp), bound, diff)
         return r
 
+    # -- SEAL-shaped composites
+    def dyadic_multiply(self, op1, op2, n, moduli):
+        return _dyadic_call(self.L.orc_dyadic_multiply, op1, op2, n, moduli)
+
+    def key_switch(self, result, t_target, n, decomp, key_mod, rns, kcc, moduli, keys, modswitch):
+        return _key_switch_call(self.L.orc_key_switch, result, t_target, n, decomp, key_mod, rns, kcc,
+                                moduli, keys, modswitch)
+
+
+def _key_switch_call(fn, result, t_target, n, decomp, key_mod, rns, kcc, moduli, keys, modswitch):
+    """shared marshalling for the two checkers: numpy in, result updated in place"""
+    keys = [np.ascontiguousarray(k, dtype=np.uint64) for k in keys]
+    kp = (vp * len(keys))(*[k.ctypes.data for k in keys])
+    moduli = np.ascontiguousarray(moduli, dtype=np.uint64)
+    modswitch = np.ascontiguousarray(modswitch, dtype=np.uint64)
+    t_target = np.ascontiguousarray(t_target, dtype=np.uint64)
+    fn(_ptr(result), _ptr(t_target), n, decomp, key_mod, rns, kcc, _ptr(moduli), kp, _ptr(modswitch))
+    return result
+
+
+def _dyadic_call(fn, op1, op2, n, moduli):
+    op1 = np.ascontiguousarray(op1, dtype=np.uint64)
+    op2 = np.ascontiguousarray(op2, dtype=np.uint64)
+    moduli = np.ascontiguousarray(moduli, dtype=np.uint64)
+    out = np.zeros(3 * n * len(moduli), dtype=np.uint64)
+    fn(_ptr(out), _ptr(op1), _ptr(op2), n, _ptr(moduli), len(moduli))
+    return out
+
 
 class Ref:
     """ctypes view of the compiled reference (kind = "reference").
@@ -253,6 +283,10 @@ class Ref:
         L.ref_eltwise_reduce_mod_native.argtypes = [vp, vp, u64, u64, u64, u64]
         L.ref_eltwise_cmp_add_native.argtypes = [vp, vp, u64, C.c_int, u64, u64]
         L.ref_eltwise_cmp_sub_mod_native.argtypes = [vp, vp, u64, u64, C.c_int, u64, u64]
+        self.has_seal = hasattr(L, "ref_key_switch")
+        if self.has_seal:
+            L.ref_dyadic_multiply.argtypes = [vp, vp, vp, u64, vp, u64]
+            L.ref_key_switch.argtypes = [vp, vp, u64, u64, u64, u64, u64, vp, vp, vp]
         self._ntt = {}
 
     def tier(self, q: int) -> str:
@@ -403,6 +437,11 @@ class Ref:
         else:
             self.L.ref_eltwise_cmp_sub_mod(_ptr(r), _ptr(a), n, q, int(cmp), bound, diff, rows, threads)
         return r
+
+
+Ref.dyadic_multiply = lambda self, op1, op2, n, moduli: _dyadic_call(self.L.ref_dyadic_multiply, op1, op2, n, moduli)
+Ref.key_switch = lambda self, result, t_target, n, decomp, key_mod, rns, kcc, moduli, keys, modswitch: _key_switch_call(
+    self.L.ref_key_switch, result, t_target, n, decomp, key_mod, rns, kcc, moduli, keys, modswitch)
 
 
 def best_checker():

@@ -489,3 +489,134 @@ void orc_eltwise_cmp_sub_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_
     r[i] = hit ? orc_sub_mod(x, diff, q) : x;
   }
 }
+
+/* ------------------------------------------------------------ SEAL composites */
+
+/* hexl/experimental/seal/dyadic-multiply-internal.cpp:17-73: ciphertext tensor
+ * product (x0*y0, x0*y1 + x1*y0, x1*y1) per RNS modulus.  Polynomial p of an
+ * operand starts at p*n*num_moduli; modulus i at i*n inside it.  Each output
+ * element is computed from its four inputs before anything is stored, so result
+ * may alias operand1 and/or operand2 (test-dyadic-multiply.cpp:38-112). */
+void orc_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                         uint64_t n, const uint64_t* moduli, uint64_t num_moduli) {
+  const uint64_t poly = n * num_moduli;
+  for (uint64_t i = 0; i < num_moduli; ++i) {
+    const uint64_t q = moduli[i];
+    for (uint64_t l = 0; l < n; ++l) {
+      const uint64_t o = i * n + l;
+      const uint64_t x0 = operand1[o], x1 = operand1[o + poly], y0 = operand2[o], y1 = operand2[o + poly];
+      const uint64_t r0 = orc_multiply_mod(x0, y0, q), r2 = orc_multiply_mod(x1, y1, q);
+      const uint64_t r1 = orc_add_mod(orc_multiply_mod(x0, y1, q), orc_multiply_mod(x1, y0, q), q);
+      result[o] = r0;
+      result[o + poly] = r1;
+      result[o + 2 * poly] = r2;
+    }
+  }
+}
+
+/* per-modulus NTT tables for the composite below */
+typedef struct {
+  uint64_t q, *w, *wp, *iw, *iwp;
+} ks_ntt;
+
+static ks_ntt ks_ntt_make(uint64_t n, uint64_t q) {
+  ks_ntt t;
+  t.q = q;
+  t.w = (uint64_t*)malloc(4 * n * sizeof(uint64_t));
+  t.wp = t.w + n;
+  t.iw = t.w + 2 * n;
+  t.iwp = t.w + 3 * n;
+  orc_ntt_tables(n, q, orc_minimal_primitive_root(2 * n, q), t.w, t.wp, t.iw, t.iwp);
+  return t;
+}
+
+/* hexl/experimental/seal/key-switch-internal.cpp:25-201 (CKKS key switching, the
+ * reference's in-tree composite of the whole hot path), step for step:
+ *   1. :49-55   every decomposition digit back to coefficient form: InvNTT(2,1)
+ *   2. :60-131  for each RNS modulus i (key_index = last key modulus for the
+ *               special prime): digits j != i are reduced mod q_key (only if
+ *               q_j > q_key, :77-85), forward-transformed lazily (4,4) (:88);
+ *               digit i itself is used in NTT form as given (:67-68); products
+ *               with the switching keys accumulate in 128 bits (:93-114) and are
+ *               reduced once (:120-130)
+ *   3. :134-198 per key component: special-prime part back to coefficients
+ *               InvNTT(2,2), + qk/2, Barrett (:141-153); for each q_i: reduce
+ *               mod q_i (:162-170), + (q_i - (qk/2 mod q_i)) (:173-178), FwdNTT(4,4)
+ *               (:181), (prod + 4 q_i - that) * qk^-1 mod q_i by FMAMod with
+ *               in_mf 8 (:187-191), modular add into result (:196-197). */
+void orc_key_switch(uint64_t* result, const uint64_t* t_target_in, uint64_t n, uint64_t decomp,
+                    uint64_t key_modulus_size, uint64_t rns, uint64_t kcc, const uint64_t* moduli,
+                    const uint64_t* const* keys, const uint64_t* modswitch_factors) {
+  ks_ntt* ntt = (ks_ntt*)malloc(key_modulus_size * sizeof(ks_ntt));
+  for (uint64_t i = 0; i < key_modulus_size; ++i) ntt[i] = ks_ntt_make(n, moduli[i]);
+  uint64_t* t_target = (uint64_t*)malloc(n * decomp * sizeof(uint64_t));
+  memcpy(t_target, t_target_in, n * decomp * sizeof(uint64_t));
+  uint64_t* t_ntt = (uint64_t*)malloc(n * sizeof(uint64_t));
+  uint64_t* prod = (uint64_t*)calloc(kcc * n * rns, sizeof(uint64_t));
+  u128* acc = (u128*)malloc(kcc * n * sizeof(u128));
+
+  for (uint64_t j = 0; j < decomp; ++j)
+    orc_ntt_inverse(t_target + j * n, t_target + j * n, n, moduli[j], ntt[j].iw, ntt[j].iwp, 2, 1, 1, 1);
+
+  for (uint64_t i = 0; i < rns; ++i) {
+    const uint64_t key_index = (i == decomp) ? key_modulus_size - 1 : i;
+    const uint64_t qk = moduli[key_index];
+    for (uint64_t x = 0; x < kcc * n; ++x) acc[x] = 0;
+    for (uint64_t j = 0; j < decomp; ++j) {
+      const uint64_t* operand;
+      if (i == j) {
+        operand = t_target_in + j * n;
+      } else {
+        if (moduli[j] <= qk)
+          memcpy(t_ntt, t_target + j * n, n * sizeof(uint64_t));
+        else
+          orc_eltwise_reduce_mod(t_ntt, t_target + j * n, n, qk, qk, 1);
+        orc_ntt_forward(t_ntt, t_ntt, n, qk, ntt[key_index].w, ntt[key_index].wp, 4, 4, 1, 1);
+        operand = t_ntt;
+      }
+      for (uint64_t k = 0; k < kcc; ++k)
+        for (uint64_t l = 0; l < n; ++l)
+          acc[k * n + l] += (u128)operand[l] * keys[j][n * key_index + k * key_modulus_size * n + l];
+    }
+    for (uint64_t k = 0; k < kcc; ++k)
+      for (uint64_t l = 0; l < n; ++l) prod[n * rns * k + i * n + l] = (uint64_t)(acc[k * n + l] % qk);
+  }
+
+  const uint64_t qlast = moduli[key_modulus_size - 1], qlast_half = qlast >> 1;
+  const ks_ntt* nlast = &ntt[key_modulus_size - 1];
+  for (uint64_t k = 0; k < kcc; ++k) {
+    uint64_t* pk = prod + k * n * rns;
+    uint64_t* t_last = pk + decomp * n;
+    orc_ntt_inverse(t_last, t_last, n, qlast, nlast->iw, nlast->iwp, 2, 2, 1, 1);
+    const uint64_t mu_last = orc_multiply_factor(1, 64, qlast);
+    for (uint64_t l = 0; l < n; ++l) {
+      uint64_t x = t_last[l] + qlast_half;
+      x = x - mulhi64(x, mu_last) * qlast;
+      t_last[l] = x >= qlast ? x - qlast : x;
+    }
+    for (uint64_t i = 0; i < decomp; ++i) {
+      const uint64_t qi = moduli[i];
+      if (qlast > qi)
+        orc_eltwise_reduce_mod(t_ntt, t_last, n, qi, qi, 1);
+      else
+        memcpy(t_ntt, t_last, n * sizeof(uint64_t));
+      const uint64_t mu_i = orc_multiply_factor(1, 64, qi);
+      uint64_t half_mod = qlast_half - mulhi64(qlast_half, mu_i) * qi;
+      if (half_mod >= qi) half_mod -= qi;
+      const uint64_t fix = qi - half_mod;
+      for (uint64_t l = 0; l < n; ++l) t_ntt[l] += fix;
+      orc_ntt_forward(t_ntt, t_ntt, n, qi, ntt[i].w, ntt[i].wp, 4, 4, 1, 1);
+      uint64_t* ith = pk + i * n;
+      for (uint64_t l = 0; l < n; ++l) ith[l] = ith[l] + (qi << 2) - t_ntt[l];
+      orc_eltwise_fma_mod(ith, ith, modswitch_factors[i], NULL, n, qi, 8);
+      uint64_t* dst = result + n * (decomp * k + i);
+      orc_eltwise_add_mod(dst, dst, ith, n, qi);
+    }
+  }
+  for (uint64_t i = 0; i < key_modulus_size; ++i) free(ntt[i].w);
+  free(ntt);
+  free(t_target);
+  free(t_ntt);
+  free(prod);
+  free(acc);
+}

@@ -58,6 +58,14 @@ void orc_eltwise_cmp_add(uint64_t* r, const uint64_t* a, uint64_t n, int cmp, ui
 void orc_eltwise_cmp_sub_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_t q, int cmp,
                              uint64_t bound, uint64_t diff);
 
+/* SEAL-shaped composites (reference: hexl/experimental/seal/) */
+void orc_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                         uint64_t n, const uint64_t* moduli, uint64_t num_moduli);
+void orc_key_switch(uint64_t* result, const uint64_t* t_target, uint64_t n, uint64_t decomp_modulus_size,
+                    uint64_t key_modulus_size, uint64_t rns_modulus_size, uint64_t key_component_count,
+                    const uint64_t* moduli, const uint64_t* const* k_switch_keys,
+                    const uint64_t* modswitch_factors);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,8 @@
 #include "hexl/eltwise/eltwise-mult-mod.hpp"
 #include "hexl/eltwise/eltwise-reduce-mod.hpp"
 #include "hexl/eltwise/eltwise-sub-mod.hpp"
+#include "hexl/experimental/seal/dyadic-multiply.hpp"
+#include "hexl/experimental/seal/key-switch.hpp"
 #include "hexl/ntt/ntt.hpp"
 #include "hexl/number-theory/number-theory.hpp"
 #include "hexl/util/util.hpp"
@@ -269,6 +271,20 @@ void ref_eltwise_cmp_sub_mod_native(uint64_t* r, const uint64_t* a, uint64_t n,
                                     uint64_t q, int cmp, uint64_t bound,
                                     uint64_t diff) {
   EltwiseCmpSubModNative(r, a, n, q, static_cast<CMPINT>(cmp), bound, diff);
+}
+
+// ---- SEAL-shaped composites (hexl/include/hexl/experimental/seal/*.hpp) --------
+void ref_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                         uint64_t n, const uint64_t* moduli, uint64_t num_moduli) {
+  DyadicMultiply(result, operand1, operand2, n, moduli, num_moduli);
+}
+void ref_key_switch(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n,
+                    uint64_t decomp_modulus_size, uint64_t key_modulus_size,
+                    uint64_t rns_modulus_size, uint64_t key_component_count,
+                    const uint64_t* moduli, const uint64_t** k_switch_keys,
+                    const uint64_t* modswitch_factors) {
+  KeySwitch(result, t_target_iter_ptr, n, decomp_modulus_size, key_modulus_size, rns_modulus_size,
+            key_component_count, moduli, k_switch_keys, modswitch_factors);
 }
 
 }  // extern "C"

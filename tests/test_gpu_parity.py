@@ -379,3 +379,81 @@ def test_cpp_drop_in_caller_runs(hb, tmp_path):
                     "-L", libdir, "-lhexl_b200", f"-Wl,-rpath,{libdir}"], check=True)
     res = subprocess.run([str(exe), "run"], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout + res.stderr
+
+
+# ---------------------------------------------- SEAL-shaped composites
+def _seal_kats():
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return json.load(open(os.path.join(root, "tests", "golden", "seal_kats.json")))
+
+
+def test_dyadic_multiply_reference_kats(hb):
+    """test/experimental/seal/test-dyadic-multiply.cpp:16-155, incl. result aliasing operand1/2"""
+    for c in _seal_kats()["dyadic_multiply"]["cases"]:
+        n, mods = c["coeff_count"], c["moduli"]
+        bufs = {"op1": np.array(c["op1"], dtype=np.uint64)}
+        bufs["op2"] = np.array(c["op2"], dtype=np.uint64) if c["op2"] is not None else None
+        bufs["out"] = np.zeros(3 * n * len(mods), dtype=np.uint64)
+        exp = np.array(c["exp_out"], dtype=np.uint64)
+        # host pointers, same aliasing as the reference test
+        h = {k: (None if v is None else v.copy()) for k, v in bufs.items()}
+        hb.DyadicMultiply(h[c["call"]["result"]], h[c["call"]["operand1"]], h[c["call"]["operand2"]], n, mods)
+        assert (h[c["call"]["result"]] == exp).all(), c["name"]
+        # device pointers
+        d = {k: (None if v is None else dev(v)) for k, v in bufs.items()}
+        hb.DyadicMultiply(d[c["call"]["result"]], d[c["call"]["operand1"]], d[c["call"]["operand2"]], n, mods)
+        assert (host(d[c["call"]["result"]]) == exp).all(), c["name"]
+
+
+def test_dyadic_multiply_matches_oracle(hb, checker):
+    n = 1 << 13
+    mods = hb.GeneratePrimes(3, 50, True, n) + hb.GeneratePrimes(2, 60, True, n)
+    a = np.concatenate([uniform_below(10 + i, n, q) for _ in range(2) for i, q in enumerate(mods)])
+    b = np.concatenate([uniform_below(20 + i, n, q) for _ in range(2) for i, q in enumerate(mods)])
+    exp = checker.dyadic_multiply(a, b, n, mods)
+    out = torch.zeros(3 * n * len(mods), dtype=torch.int64, device="cuda")
+    hb.DyadicMultiply(out, dev(a), dev(b), n, mods)
+    assert (host(out) == exp).all()
+
+
+def test_key_switch_reference_kat(hb):
+    """test/experimental/seal/test-key-switch.cpp:16-186 through host and device pointers"""
+    k = _seal_kats()["key_switch"]
+    args = (k["coeff_count"], k["decomp_modulus_size"], k["key_modulus_size"], k["rns_modulus_size"],
+            k["key_component_count"], k["moduli"])
+    exp = np.array(k["expected_output"], dtype=np.uint64)
+    keys = [np.array(x, dtype=np.uint64) for x in k["k_switch_keys"]]
+    res = np.array(k["input"], dtype=np.uint64)
+    hb.KeySwitch(res, np.array(k["t_target_iter_ptr"], dtype=np.uint64), *args, keys, k["modswitch_factors"])
+    assert (res == exp).all()
+    dres = dev(np.array(k["input"], dtype=np.uint64))
+    hb.KeySwitch(dres, dev(np.array(k["t_target_iter_ptr"], dtype=np.uint64)), *args, [dev(x) for x in keys],
+                 k["modswitch_factors"])
+    assert (host(dres) == exp).all()
+
+
+@pytest.mark.parametrize("logn,decomp,bits", [(12, 3, 50), (13, 4, 58), (15, 6, 50)])
+def test_key_switch_matches_oracle(hb, checker, logn, decomp, bits):
+    """CKKS key-switch shape of BASELINE config 5 (N = 2^15, many RNS moduli) against the
+    compiled reference / oracle on random data."""
+    n = 1 << logn
+    kms = rns = decomp + 1
+    kcc = 2
+    mods = hb.GeneratePrimes(kms, bits, True, n)
+    t_target = np.concatenate([uniform_below(30 + j, n, mods[j]) for j in range(decomp)])
+    keys = [np.concatenate([uniform_below(100 * j + 7 * k + i, n, mods[i]) for k in range(kcc) for i in range(kms)])
+            for j in range(decomp)]
+    result = np.concatenate([uniform_below(500 + 10 * k + i, n, mods[i]) for k in range(kcc) for i in range(decomp)])
+    modswitch = [hb.InverseMod(mods[-1] % mods[i], mods[i]) for i in range(decomp)]
+    exp = checker.key_switch(result.copy(), t_target, n, decomp, kms, rns, kcc, mods, keys, modswitch)
+    dres = dev(result)
+    hb.KeySwitch(dres, dev(t_target), n, decomp, kms, rns, kcc, mods, [dev(x) for x in keys], modswitch)
+    assert (host(dres) == exp).all()
+
+
+def test_ntt_cache(hb):
+    q = hb.GeneratePrimes(1, 40, True, 1024)[0]
+    a, b = hb.GetNTT(1024, q), hb.GetNTT(1024, q)
+    assert a._h.value == b._h.value and a.GetModulus() == q

@@ -96,3 +96,27 @@ def test_eltwise_kats(port, kats):
     for c in kats["eltwise_cmp_sub_mod"]["cases"]:
         out = port.cmp_sub_mod(kat_values(c["op1"], 0), c["q"], c["cmp"], c["bound"], c["diff"])
         assert (out == kat_values(c["out"], 0)).all()
+
+
+def _seal_kats():
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return json.load(open(os.path.join(root, "tests", "golden", "seal_kats.json")))
+
+
+def test_seal_composite_kats(port):
+    """KeySwitch (test/experimental/seal/test-key-switch.cpp:16-186) and DyadicMultiply
+    (test-dyadic-multiply.cpp:16-155) known answers pin the oracle's composites."""
+    d = _seal_kats()
+    k = d["key_switch"]
+    res = np.array(k["input"], dtype=np.uint64)
+    port.key_switch(res, k["t_target_iter_ptr"], k["coeff_count"], k["decomp_modulus_size"], k["key_modulus_size"],
+                    k["rns_modulus_size"], k["key_component_count"], k["moduli"], k["k_switch_keys"],
+                    k["modswitch_factors"])
+    assert (res == np.array(k["expected_output"], dtype=np.uint64)).all()
+    for c in d["dyadic_multiply"]["cases"]:
+        n, nm = c["coeff_count"], len(c["moduli"])
+        op2 = c["op2"] if c["op2"] is not None else c["op1"]
+        out = port.dyadic_multiply(c["op1"][:2 * n * nm], op2[:2 * n * nm], n, c["moduli"])
+        assert (out == np.array(c["exp_out"], dtype=np.uint64)).all(), c["name"]

@@ -79,3 +79,24 @@ def test_eltwise_port_matches_reference(port, ref, bits):
             bound = int(w[3])
             assert (port.cmp_sub_mod(w, q, cmp, bound, diff)
                     == ref.cmp_sub_mod(w, q, cmp, bound, diff, native=native)).all()
+
+
+@pytest.mark.parametrize("logn,decomp,bits", [(4, 2, 59), (10, 3, 50), (13, 5, 58)])
+def test_key_switch_port_matches_reference(port, ref, logn, decomp, bits):
+    if not ref.has_seal:
+        pytest.skip("oracle/_ref was built without the experimental/seal sources")
+    n = 1 << logn
+    kms = rns = decomp + 1
+    kcc = 2
+    mods = ref.generate_primes(kms, bits, True, n)
+    t_target = np.concatenate([uniform_below(30 + j, n, mods[j]) for j in range(decomp)])
+    keys = [np.concatenate([uniform_below(100 * j + 7 * k + i, n, mods[i]) for k in range(kcc) for i in range(kms)])
+            for j in range(decomp)]
+    result = np.concatenate([uniform_below(500 + 10 * k + i, n, mods[i]) for k in range(kcc) for i in range(decomp)])
+    modswitch = [ref.inverse_mod(mods[-1] % mods[i], mods[i]) for i in range(decomp)]
+    a = port.key_switch(result.copy(), t_target, n, decomp, kms, rns, kcc, mods, keys, modswitch)
+    b = ref.key_switch(result.copy(), t_target, n, decomp, kms, rns, kcc, mods, keys, modswitch)
+    assert (a == b).all()
+    x = np.concatenate([uniform_below(1 + i, n, q) for _ in range(2) for i, q in enumerate(mods)])
+    y = np.concatenate([uniform_below(9 + i, n, q) for _ in range(2) for i, q in enumerate(mods)])
+    assert (port.dyadic_multiply(x, y, n, mods) == ref.dyadic_multiply(x, y, n, mods)).all()
