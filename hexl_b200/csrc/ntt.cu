@@ -383,6 +383,9 @@ __device__ __forceinline__ void inv_passes(u64 (&v)[16], u64* srow, unsigned u, 
 #ifndef HEXL_B200_ROW_MIN_BLOCKS
 #define HEXL_B200_ROW_MIN_BLOCKS 3
 #endif
+#ifndef HEXL_B200_ROW_MIN_BLOCKS_512
+#define HEXL_B200_ROW_MIN_BLOCKS_512 2
+#endif
 
 template <int LOGC>
 struct RowCfg {
@@ -394,7 +397,7 @@ struct RowCfg {
   static constexpr bool TW_TABLES = LOGC >= 8;          // sub-tree twiddles staged in shared memory
   static constexpr size_t ROW_BYTES = (size_t)C * sizeof(u64) + (TW_TABLES ? kRowTwEntries * sizeof(Twiddle) : 0);
   static constexpr size_t SMEM = (size_t)ROWS * ROW_BYTES;
-  static constexpr int MIN_BLOCKS = THREADS <= 256 ? HEXL_B200_ROW_MIN_BLOCKS : 1;
+  static constexpr int MIN_BLOCKS = THREADS <= 256 ? HEXL_B200_ROW_MIN_BLOCKS : (THREADS == 512 ? HEXL_B200_ROW_MIN_BLOCKS_512 : 1);
 };
 
 // Global-memory access policies for coefficients.  Streaming (evict-first) for
