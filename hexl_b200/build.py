@@ -30,7 +30,7 @@ HEADERS = ["internal.h", "modarith.cuh", "numtheory.h", os.path.join(ROOT, "incl
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-std=c++17", "-O3", "-lineinfo",
+    "-std=c++17", "-O3", "-lineinfo", "-diag-suppress=177",
     "-Xcompiler", "-fPIC,-Wall",
     "-Xptxas", "-v",
 ]

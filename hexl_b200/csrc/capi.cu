@@ -45,6 +45,8 @@ struct hexl_b200_ntt {
   struct Dev {
     Twiddle* fwd = nullptr;
     Twiddle* inv = nullptr;
+    Twiddle32* fwd32 = nullptr;  // q < 2^30 only
+    Twiddle32* inv32 = nullptr;
   };
   std::map<int, Dev> dev;  // device ordinal -> uploaded tables
 };
@@ -296,6 +298,7 @@ bool check_ntt_arguments(uint64_t degree, uint64_t q, const char** why) {
 }
 
 Twiddle make_twiddle(uint64_t v, uint64_t q) { return Twiddle{v, nt::multiply_factor(v, 64, q)}; }
+Twiddle32 make_twiddle32(uint64_t v, uint64_t q) { return Twiddle32{(uint32_t)v, (uint32_t)((v << 32) / q)}; }
 
 // hexl/ntt/ntt-internal.cpp:54-169 restated: psi^i goes to slot bitrev(i); the
 // inverse powers are additionally listed in the order the reference's inverse
@@ -344,10 +347,25 @@ int device_tables(hexl_b200_ntt* h, int dev, NttDeviceTables* out) {
     CU(cudaMalloc(&d.inv, bytes));
     CU(cudaMemcpy(d.fwd, h->fwd_tree.data(), bytes, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d.inv, h->inv_tree.data(), bytes, cudaMemcpyHostToDevice));
+    if (h->q < kSmallModulusLimit) {
+      std::vector<Twiddle32> f32(h->n), i32(h->n);
+      for (uint64_t k = 0; k < h->n; ++k) {
+        f32[k] = make_twiddle32(h->fwd_tree[k].w, h->q);
+        i32[k] = make_twiddle32(h->inv_tree[k].w, h->q);
+      }
+      CU(cudaMalloc(&d.fwd32, h->n * sizeof(Twiddle32)));
+      CU(cudaMalloc(&d.inv32, h->n * sizeof(Twiddle32)));
+      CU(cudaMemcpy(d.fwd32, f32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(d.inv32, i32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
+    }
     it = h->dev.emplace(dev, d).first;
   }
   out->fwd = it->second.fwd;
   out->inv = it->second.inv;
+  out->fwd32 = it->second.fwd32;
+  out->inv32 = it->second.inv32;
+  out->inv_n32 = h->q < kSmallModulusLimit ? make_twiddle32(h->inv_n.w, h->q) : Twiddle32{0, 0};
+  out->inv_n_w32 = h->q < kSmallModulusLimit ? make_twiddle32(h->inv_n_w.w, h->q) : Twiddle32{0, 0};
   out->n = h->n;
   out->log_n = h->log_n;
   out->q = h->q;
@@ -710,6 +728,8 @@ void hexl_b200_ntt_release(hexl_b200_ntt* h) {
     if (cudaSetDevice(kv.first) == cudaSuccess) {
       cudaFree(kv.second.fwd);
       cudaFree(kv.second.inv);
+      cudaFree(kv.second.fwd32);  // nullptr unless q < 2^30
+      cudaFree(kv.second.inv32);
     }
   }
   if (prev >= 0) cudaSetDevice(prev);

@@ -40,13 +40,17 @@ cudaError_t launch_eltwise(EltOp op, const EltParams& p, cudaStream_t stream);
 struct NttDeviceTables {
   const Twiddle* fwd;
   const Twiddle* inv;
+  const Twiddle32* fwd32;  // 32-bit copies of both tables, only for q < 2^30 (else nullptr)
+  const Twiddle32* inv32;
   u64 n;
   int log_n;
   u64 q;
   u64 mu;           // floor(2^64 / q)
   Twiddle inv_n;    // N^-1 and its Shoup factor
   Twiddle inv_n_w;  // N^-1 * inv[1] and its Shoup factor
+  Twiddle32 inv_n32, inv_n_w32;
 };
+constexpr u64 kSmallModulusLimit = 1ull << 30;  // below: 4q < 2^32, the 32-bit kernels apply
 
 // result/operand: `batch` polynomials back to back on the current device.
 cudaError_t launch_ntt_forward(const NttDeviceTables& t, u64* result, const u64* operand,

@@ -21,6 +21,12 @@ struct __align__(16) Twiddle {
   u64 w;
   u64 wp;
 };
+// the same for moduli below 2^30, where every lazy value fits one 32-bit word:
+// {w, floor(w * 2^32 / q)}, one 64-bit load
+struct __align__(8) Twiddle32 {
+  uint32_t w;
+  uint32_t wp;
+};
 
 __device__ __forceinline__ u64 mulhi(u64 a, u64 b) {
   return __umul64hi((unsigned long long)a, (unsigned long long)b);

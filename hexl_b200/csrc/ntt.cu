@@ -56,9 +56,28 @@ namespace {
 //    register bit) or 8*2^K q (all-sum slots), and only slots above 8q are
 //    Barrett-reduced at the pass boundary (4 of 16 for a 4-stage pass).  The
 //    largest transient is 2 * 8*2^4 * q = 256q < 2^64 for q < 2^56.
-//  Both modes produce the same canonical values; lazy outputs (out_mf 4 / 2)
+//
+//  SMALL (q < 2^30): 4q < 2^32, so every lazy value is ONE 32-bit word.  Same Harvey
+//    butterflies as GENERIC with beta = 2^32 (twiddle pairs {w, floor(w 2^32/q)}):
+//    one IMAD.WIDE + two IMADs per twiddle product instead of 6 + 4, conditional
+//    subtraction as min(x, x - 2q).  Registers and shared memory hold 32-bit words
+//    (global memory keeps the API's 64-bit coefficients); at ~1/4 of the multiplier
+//    work these kernels are HBM-bound.
+//  All modes produce the same canonical values; lazy outputs (out_mf 4 / 2)
 //  are congruent and inside the advertised range.
-enum : int { kGeneric = 0, kFast = 1 };
+enum : int { kGeneric = 0, kFast = 1, kSmall = 2 };
+
+// element and twiddle types of a mode
+template <int MODE>
+struct Ar {
+  using E = u64;
+  using Tw = Twiddle;
+};
+template <>
+struct Ar<kSmall> {
+  using E = unsigned;
+  using Tw = Twiddle32;
+};
 constexpr u64 kFastModulusLimit = 1ull << 56;
 constexpr int kFastProd = 4;   // FAST: a twiddle product is < 4q
 constexpr int kFastBound = 8;  // FAST inverse: every value is < 8q at a pass boundary
@@ -102,6 +121,13 @@ __device__ __forceinline__ unsigned mad_lo(unsigned a, unsigned b, unsigned c) {
 __device__ __forceinline__ Twiddle ld_tw(const Twiddle* p) {
   const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));
   Twiddle t;
+  t.w = v.x;
+  t.wp = v.y;
+  return t;
+}
+__device__ __forceinline__ Twiddle32 ld_tw(const Twiddle32* p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  Twiddle32 t;
   t.w = v.x;
   t.wp = v.y;
   return t;
@@ -217,6 +243,44 @@ __device__ __forceinline__ u64 inv_out(u64 v, const Mod& m, int out_mf) {
   return out_mf == 1 ? csub(v, m.q) : v;
 }
 
+// ---- SMALL mode (q < 2^30): the same butterflies on 32-bit words
+__device__ __forceinline__ unsigned csub32(unsigned x, unsigned c) { return min(x, x - c); }  // x < 2c
+// x*w mod q in [0,2q) for any 32-bit x:  x*w - hi32(x*wp)*q  (mod 2^32)
+__device__ __forceinline__ unsigned mul_tw32(unsigned x, const Twiddle32 w, const Mod& m) {
+  const unsigned Q = hi32(mul_wide(x, w.wp));
+  return mad_lo(Q, m.n0, x * w.w);  // n0 = low word of 2^64 - q = 2^32 - q
+}
+template <int MODE>
+__device__ __forceinline__ void fwd_bfly(unsigned& X, unsigned& Y, const Twiddle32 w, const Mod& m) {
+  const unsigned two_q = lo32(m.two_q);
+  const unsigned tx = csub32(X, two_q);
+  const unsigned T = mul_tw32(Y, w, m);
+  X = tx + T;
+  Y = tx + two_q - T;
+}
+template <int MODE>
+__device__ __forceinline__ void inv_bfly(unsigned& X, unsigned& Y, const Twiddle32 w, const Mod& m, unsigned) {
+  const unsigned two_q = lo32(m.two_q);
+  const unsigned s = X + Y;
+  const unsigned d = X + two_q - Y;
+  X = csub32(s, two_q);
+  Y = mul_tw32(d, w, m);
+}
+__device__ __forceinline__ void inv_bfly_last(unsigned& X, unsigned& Y, const Twiddle32 inv_n,
+                                              const Twiddle32 inv_n_w, const Mod& m, unsigned) {
+  const unsigned s = X + Y;
+  const unsigned d = X + lo32(m.two_q) - Y;
+  X = mul_tw32(s, inv_n, m);
+  Y = mul_tw32(d, inv_n_w, m);
+}
+template <int MODE>
+__device__ __forceinline__ unsigned fwd_out(unsigned v, const Mod& m, int out_mf) {
+  return out_mf == 1 ? csub32(csub32(v, lo32(m.two_q)), lo32(m.q)) : v;
+}
+__device__ __forceinline__ unsigned inv_out(unsigned v, const Mod& m, int out_mf) {
+  return out_mf == 1 ? csub32(v, lo32(m.q)) : v;
+}
+
 // FAST inverse bookkeeping.  After K unreduced GS stages on register bits 0..K-1
 // of values that all started below kFastBound*q, the slot whose low K bits are
 // `low` is bounded by (in units of q):
@@ -229,6 +293,12 @@ __host__ __device__ constexpr int inv_slot_bound(int K, int low) {
 }
 // the largest Y entering GS stage s of such a pass (what cq must cover)
 __host__ __device__ constexpr int inv_stage_cover(int s) { return kFastBound << s; }
+// the multiple of q added before the subtraction of inverse stage `step` of a pass
+template <int MODE>
+__device__ __forceinline__ typename Ar<MODE>::E stage_cq(int step, const Mod& m) {
+  if (MODE == kFast) return (u64)inv_stage_cover(step) * m.q;
+  return (typename Ar<MODE>::E)m.two_q;
+}
 
 template <int K, int NSLOTS, int E = 0>
 __device__ __forceinline__ void inv_pass_fixup(u64* v, const Mod& m) {
@@ -243,7 +313,12 @@ __device__ __forceinline__ void inv_pass_fixup(u64* v, const Mod& m) {
 // (low 4 bits) with the next 4 bits.  Conflict-free (per half-warp) for every
 // access pattern of the passes below; a bijection inside each aligned block of
 // 16 elements.
-__device__ __forceinline__ unsigned swz(unsigned j) { return j ^ ((j >> 4) & 15u); }
+// For 32-bit elements (SMALL mode) the same shift with a 5-bit mask spreads the 32
+// lanes of a warp over the 32 four-byte banks (tests/test_kernel_model.py checks both).
+template <typename E>
+__device__ __forceinline__ unsigned swz(unsigned j) {
+  return j ^ ((j >> 4) & (sizeof(E) == 8 ? 15u : 31u));
+}
 
 // Coefficient index held in register slot e of thread u when the 4 register
 // bits sit at bit position LB of the row-local index.
@@ -270,9 +345,8 @@ struct PassTw {
   static constexpr int kOffset = kDepth == 0 ? 0 : 16;
 };
 
-template <int LOGC>
-__device__ __forceinline__ void load_row_twiddles(Twiddle* stab, unsigned u, u64 base,
-                                                  const Twiddle* __restrict__ tw) {
+template <int LOGC, typename Tw>
+__device__ __forceinline__ void load_row_twiddles(Tw* stab, unsigned u, u64 base, const Tw* __restrict__ tw) {
   constexpr int T = (1 << LOGC) / 16;
   for (int idx = u; idx < kRowTwEntries; idx += T) {
     const int l = idx & 15;
@@ -286,12 +360,14 @@ __device__ __forceinline__ void load_row_twiddles(Twiddle* stab, unsigned u, u64
 // Butterfly stages on row-local index bits HB..LOB (all inside [LB, LB+3]).
 // FWD: bits descend (CT).  INV: bits ascend (GS), LOB == LB.
 template <int MODE, int LOGC, int LB, int HB, int LOB, bool FWD>
-__device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
-                                           const Twiddle* __restrict__ tw, const Twiddle* stab,
-                                           const Mod& m, bool fold, Twiddle inv_n, Twiddle inv_n_w) {
+__device__ __forceinline__ void reg_stages(typename Ar<MODE>::E (&v)[16], unsigned u, u64 base,
+                                           const typename Ar<MODE>::Tw* __restrict__ tw,
+                                           const typename Ar<MODE>::Tw* stab, const Mod& m, bool fold,
+                                           typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w) {
   using PT = PassTw<LOGC, LB, HB, LOB>;
-  const Twiddle* sroot = stab + PT::kOffset + ((u >> LB) << 4);  // this thread's sub-tree table
-  Twiddle wc[8];
+  using Tw = typename Ar<MODE>::Tw;
+  const Tw* sroot = stab + PT::kOffset + ((u >> LB) << 4);  // this thread's sub-tree table
+  Tw wc[8];
   auto stage_node0 = [&](int step) {
     const int beta = FWD ? HB - step : LOB + step;
     return (base << (LOGC - 1 - beta)) + ((u64)(u >> LB) << (LB + 3 - beta));
@@ -302,7 +378,7 @@ __device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
     const int eb = beta - LB;                       // register bit
     const int sp = LOGC - 1 - beta;                 // stage number inside the row
     // FAST inverse: multiple of q covering every Y of this stage (GENERIC: 2q)
-    const u64 cq = (!FWD && MODE == kFast) ? (u64)inv_stage_cover(step) * m.q : m.two_q;
+    const typename Ar<MODE>::E cq = stage_cq<MODE>(step, m);
     if (!FWD && sp == 0 && fold) {
       // root stage of the whole transform: one group, N^-1 folded in
 #pragma unroll
@@ -328,7 +404,9 @@ __device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
       }
     }
   }
-  if (!FWD && MODE == kFast && !(fold && LOGC - 1 - HB == 0)) inv_pass_fixup<HB - LOB + 1, 16>(v, m);
+  if constexpr (!FWD && MODE == kFast) {
+    if (!(fold && LOGC - 1 - HB == 0)) inv_pass_fixup<HB - LOB + 1, 16>(v, m);
+  }
 }
 
 // Transpose between two register layouts through shared memory.  The exchange
@@ -336,38 +414,41 @@ __device__ __forceinline__ void reg_stages(u64 (&v)[16], unsigned u, u64 base,
 // value stays inside one warp and __syncwarp() replaces the CTA barrier.  No
 // barrier is needed after the reads: the next exchange writes exactly the
 // addresses this thread has just read (same layout), which nobody else touches.
-template <int LB_FROM, int LB_TO>
-__device__ __forceinline__ void smem_exchange(u64 (&v)[16], u64* srow, unsigned u) {
+template <int LB_FROM, int LB_TO, typename E>
+__device__ __forceinline__ void smem_exchange(E (&v)[16], E* srow, unsigned u) {
   constexpr bool kWarpLocal = (LB_FROM > LB_TO ? LB_FROM : LB_TO) <= 5;
 #pragma unroll
-  for (int e = 0; e < 16; ++e) srow[swz(reg_index<LB_FROM>(u, e))] = v[e];
+  for (int e = 0; e < 16; ++e) srow[swz<E>(reg_index<LB_FROM>(u, e))] = v[e];
   if (kWarpLocal)
     __syncwarp();
   else
     __syncthreads();
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = srow[swz(reg_index<LB_TO>(u, e))];
+  for (int e = 0; e < 16; ++e) v[e] = srow[swz<E>(reg_index<LB_TO>(u, e))];
 }
 
 // Forward passes after pass 0: register bits move down by 4 per pass, clamped at 0.
 template <int MODE, int LOGC, int PASS>
-__device__ __forceinline__ void fwd_passes(u64 (&v)[16], u64* srow, unsigned u, u64 base,
-                                           const Twiddle* tw, const Twiddle* stab, const Mod& m) {
+__device__ __forceinline__ void fwd_passes(typename Ar<MODE>::E (&v)[16], typename Ar<MODE>::E* srow, unsigned u,
+                                           u64 base, const typename Ar<MODE>::Tw* tw,
+                                           const typename Ar<MODE>::Tw* stab, const Mod& m) {
+  using Tw = typename Ar<MODE>::Tw;
   constexpr int PREV_LB = (LOGC - 4 * PASS) > 0 ? (LOGC - 4 * PASS) : 0;
   constexpr int HB = LOGC - 4 * PASS - 1;  // highest index bit not yet processed
   if constexpr (HB >= 0) {
     constexpr int LB = (HB - 3) > 0 ? (HB - 3) : 0;
     smem_exchange<PREV_LB, LB>(v, srow, u);
-    reg_stages<MODE, LOGC, LB, HB, LB, true>(v, u, base, tw, stab, m, false, Twiddle{}, Twiddle{});
+    reg_stages<MODE, LOGC, LB, HB, LB, true>(v, u, base, tw, stab, m, false, Tw{}, Tw{});
     fwd_passes<MODE, LOGC, PASS + 1>(v, srow, u, base, tw, stab, m);
   }
 }
 
 // Inverse passes: mirror image.  PASS counts down; pass P-1 is done first.
 template <int MODE, int LOGC, int PASS>
-__device__ __forceinline__ void inv_passes(u64 (&v)[16], u64* srow, unsigned u, u64 base,
-                                           const Twiddle* tw, const Twiddle* stab, const Mod& m, bool fold,
-                                           Twiddle inv_n, Twiddle inv_n_w) {
+__device__ __forceinline__ void inv_passes(typename Ar<MODE>::E (&v)[16], typename Ar<MODE>::E* srow, unsigned u,
+                                           u64 base, const typename Ar<MODE>::Tw* tw,
+                                           const typename Ar<MODE>::Tw* stab, const Mod& m, bool fold,
+                                           typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w) {
   // forward pass PASS handled bits HB..LB; the inverse handles the same bits ascending
   constexpr int HB = LOGC - 4 * PASS - 1;
   constexpr int LB = (HB - 3) > 0 ? (HB - 3) : 0;
@@ -387,17 +468,23 @@ __device__ __forceinline__ void inv_passes(u64 (&v)[16], u64* srow, unsigned u, 
 #define HEXL_B200_ROW_MIN_BLOCKS_512 2
 #endif
 
-template <int LOGC>
+#ifndef HEXL_B200_ROW_MIN_BLOCKS_SMALL
+#define HEXL_B200_ROW_MIN_BLOCKS_SMALL 4
+#endif
+template <int LOGC, int MODE = kGeneric>
 struct RowCfg {
+  using E = typename Ar<MODE>::E;
+  using Tw = typename Ar<MODE>::Tw;
   static constexpr int C = 1 << LOGC;
   static constexpr int T = C / 16;                        // threads per row
   static constexpr int ROWS = T >= 256 ? 1 : 256 / T;     // rows per CTA
   static constexpr int THREADS = T * ROWS;
   static constexpr int PASSES = (LOGC + 3) / 4;
   static constexpr bool TW_TABLES = LOGC >= 8;          // sub-tree twiddles staged in shared memory
-  static constexpr size_t ROW_BYTES = (size_t)C * sizeof(u64) + (TW_TABLES ? kRowTwEntries * sizeof(Twiddle) : 0);
+  static constexpr size_t ROW_BYTES = (size_t)C * sizeof(E) + (TW_TABLES ? kRowTwEntries * sizeof(Tw) : 0);
   static constexpr size_t SMEM = (size_t)ROWS * ROW_BYTES;
-  static constexpr int MIN_BLOCKS = THREADS <= 256 ? HEXL_B200_ROW_MIN_BLOCKS : (THREADS == 512 ? HEXL_B200_ROW_MIN_BLOCKS_512 : 1);
+  static constexpr int MIN_BLOCKS = THREADS <= 256 ? (MODE == kSmall ? HEXL_B200_ROW_MIN_BLOCKS_SMALL : HEXL_B200_ROW_MIN_BLOCKS)
+                                                   : (THREADS == 512 ? HEXL_B200_ROW_MIN_BLOCKS_512 : 1);
 };
 
 // Global-memory access policies for coefficients.  Streaming (evict-first) for
@@ -419,19 +506,21 @@ __device__ __forceinline__ void st_coef(u64* p, u64 v) {
 // Forward transform of one row of C = 2^LOGC contiguous coefficients rooted at
 // tree node `base`, by the T = C/16 threads whose index in the row is u.
 template <int MODE, int LOGC, int LD, int ST>
-__device__ __forceinline__ void row_fwd_body(u64* out, const u64* in, u64* srow, unsigned u, u64 base,
-                                             const Twiddle* __restrict__ tw, const Mod& m, int out_mf,
-                                             bool active) {
-  u64 v[16];
+__device__ __forceinline__ void row_fwd_body(u64* out, const u64* in, typename Ar<MODE>::E* srow, unsigned u,
+                                             u64 base, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod& m,
+                                             int out_mf, bool active) {
+  using E = typename Ar<MODE>::E;
+  using Tw = typename Ar<MODE>::Tw;
+  E v[16];
   constexpr int LB0 = LOGC - 4;  // pass 0: register bits are the top 4 index bits
-  Twiddle* stab = reinterpret_cast<Twiddle*>(srow + (1 << LOGC));
+  Tw* stab = reinterpret_cast<Tw*>(srow + (1 << LOGC));
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = ld_coef<LD>(in + reg_index<LB0>(u, e));
+  for (int e = 0; e < 16; ++e) v[e] = (E)ld_coef<LD>(in + reg_index<LB0>(u, e));
   if constexpr (RowCfg<LOGC>::TW_TABLES) {
     load_row_twiddles<LOGC>(stab, u, base, tw);
     __syncthreads();
   }
-  reg_stages<MODE, LOGC, LB0, LOGC - 1, LB0, true>(v, u, base, tw, stab, m, false, Twiddle{}, Twiddle{});
+  reg_stages<MODE, LOGC, LB0, LOGC - 1, LB0, true>(v, u, base, tw, stab, m, false, Tw{}, Tw{});
   fwd_passes<MODE, LOGC, 1>(v, srow, u, base, tw, stab, m);
   // registers now hold 16 consecutive coefficients per thread (LB = 0)
 #pragma unroll
@@ -448,16 +537,19 @@ __device__ __forceinline__ void row_fwd_body(u64* out, const u64* in, u64* srow,
 
 // Inverse transform of one row (the last log2 C ... first stages of the GS order).
 template <int MODE, int LOGC, int LD, int ST>
-__device__ __forceinline__ void row_inv_body(u64* out, const u64* in, u64* srow, unsigned u, u64 base,
-                                             const Twiddle* __restrict__ tw, const Mod& m, int out_mf,
-                                             bool fold, Twiddle inv_n, Twiddle inv_n_w, bool active) {
+__device__ __forceinline__ void row_inv_body(u64* out, const u64* in, typename Ar<MODE>::E* srow, unsigned u,
+                                             u64 base, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod& m,
+                                             int out_mf, bool fold, typename Ar<MODE>::Tw inv_n,
+                                             typename Ar<MODE>::Tw inv_n_w, bool active) {
   using Cfg = RowCfg<LOGC>;
-  u64 v[16];
+  using E = typename Ar<MODE>::E;
+  using Tw = typename Ar<MODE>::Tw;
+  E v[16];
   constexpr int LB0 = LOGC - 4;
   constexpr int LB_IN = LB0 < 4 ? LB0 : 4;  // 16 lanes read one 128-byte line per instruction
-  Twiddle* stab = reinterpret_cast<Twiddle*>(srow + (1 << LOGC));
+  Tw* stab = reinterpret_cast<Tw*>(srow + (1 << LOGC));
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = ld_coef<LD>(in + reg_index<LB_IN>(u, e));
+  for (int e = 0; e < 16; ++e) v[e] = (E)ld_coef<LD>(in + reg_index<LB_IN>(u, e));
   if constexpr (Cfg::TW_TABLES) {
     load_row_twiddles<LOGC>(stab, u, base, tw);
     __syncthreads();  // tables are filled by other warps than the ones that read them
@@ -475,36 +567,37 @@ __device__ __forceinline__ void row_inv_body(u64* out, const u64* in, u64* srow,
 
 // One CTA = ROWS rows of C contiguous coefficients.  rows_per_poly = N / C.
 template <int MODE, int LOGC>
-__global__ void __launch_bounds__(RowCfg<LOGC>::THREADS, RowCfg<LOGC>::MIN_BLOCKS)
-    ntt_row_fwd(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m,
+__global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE>::MIN_BLOCKS)
+    ntt_row_fwd(u64* result, const u64* operand, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod m,
                 u64 total_rows, unsigned rows_per_poly, int out_mf) {
-  using Cfg = RowCfg<LOGC>;
-  extern __shared__ __align__(16) u64 smem[];
+  using Cfg = RowCfg<LOGC, MODE>;
+  extern __shared__ __align__(16) unsigned char smem[];
   const unsigned row_local = threadIdx.x / Cfg::T, u = threadIdx.x % Cfg::T;
   u64 row = (u64)blockIdx.x * Cfg::ROWS + row_local;
   const bool active = row < total_rows;
   if (!active) row = total_rows - 1;  // keep barriers uniform; stores are masked
   const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
-  row_fwd_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C,
-                                             smem + (size_t)row_local * (Cfg::ROW_BYTES / sizeof(u64)), u, base, tw, m,
-                                             out_mf, active);
+  row_fwd_body<MODE, LOGC, kStream, kStream>(
+      result + row * Cfg::C, operand + row * Cfg::C,
+      reinterpret_cast<typename Cfg::E*>(smem + (size_t)row_local * Cfg::ROW_BYTES), u, base, tw, m, out_mf, active);
 }
 
 template <int MODE, int LOGC>
-__global__ void __launch_bounds__(RowCfg<LOGC>::THREADS, RowCfg<LOGC>::MIN_BLOCKS)
-    ntt_row_inv(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m,
-                u64 total_rows, unsigned rows_per_poly, int out_mf, int fold, Twiddle inv_n,
-                Twiddle inv_n_w) {
-  using Cfg = RowCfg<LOGC>;
-  extern __shared__ __align__(16) u64 smem[];
+__global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE>::MIN_BLOCKS)
+    ntt_row_inv(u64* result, const u64* operand, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod m,
+                u64 total_rows, unsigned rows_per_poly, int out_mf, int fold, typename Ar<MODE>::Tw inv_n,
+                typename Ar<MODE>::Tw inv_n_w) {
+  using Cfg = RowCfg<LOGC, MODE>;
+  extern __shared__ __align__(16) unsigned char smem[];
   const unsigned row_local = threadIdx.x / Cfg::T, u = threadIdx.x % Cfg::T;
   u64 row = (u64)blockIdx.x * Cfg::ROWS + row_local;
   const bool active = row < total_rows;
   if (!active) row = total_rows - 1;
   const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
-  row_inv_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C,
-                                             smem + (size_t)row_local * (Cfg::ROW_BYTES / sizeof(u64)), u, base, tw, m,
-                                             out_mf, fold != 0, inv_n, inv_n_w, active);
+  row_inv_body<MODE, LOGC, kStream, kStream>(
+      result + row * Cfg::C, operand + row * Cfg::C,
+      reinterpret_cast<typename Cfg::E*>(smem + (size_t)row_local * Cfg::ROW_BYTES), u, base, tw, m, out_mf,
+      fold != 0, inv_n, inv_n_w, active);
 }
 
 // ------------------------------------------------------------- column kernel
@@ -513,24 +606,26 @@ __global__ void __launch_bounds__(RowCfg<LOGC>::THREADS, RowCfg<LOGC>::MIN_BLOCK
 // twiddles stw[1..R-1] are laid out as a local tree (node 2^s + i).
 template <int MODE, int LOGR, bool FWD, int LD, int ST>
 __device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 off, int log_stride,
-                                         const Twiddle* stw, const Mod& m, int out_mf, bool root_fold,
-                                         Twiddle inv_n, Twiddle inv_n_w) {
+                                         const typename Ar<MODE>::Tw* stw, const Mod& m, int out_mf, bool root_fold,
+                                         typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w) {
+  using E = typename Ar<MODE>::E;
+  using Tw = typename Ar<MODE>::Tw;
   constexpr int R = 1 << LOGR;
-  u64 v[R];
+  E v[R];
 #pragma unroll
-  for (int e = 0; e < R; ++e) v[e] = ld_coef<LD>(operand + off + ((u64)e << log_stride));
+  for (int e = 0; e < R; ++e) v[e] = (E)ld_coef<LD>(operand + off + ((u64)e << log_stride));
 #pragma unroll
   for (int step = 0; step < LOGR; ++step) {
     const int s = FWD ? step : LOGR - 1 - step;      // stage inside the sub-block
     const int eb = LOGR - 1 - s;                     // register bit
-    const u64 cq = (!FWD && MODE == kFast) ? (u64)inv_stage_cover(step) * m.q : m.two_q;
+    const E cq = stage_cq<MODE>(step, m);
     if (!FWD && root_fold && s == 0) {
 #pragma unroll
       for (int l = 0; l < (1 << eb); ++l) inv_bfly_last(v[l], v[l | (1 << eb)], inv_n, inv_n_w, m, cq);
     } else {
 #pragma unroll
       for (int gi = 0; gi < (1 << s); ++gi) {
-        const Twiddle w = stw[(1 << s) + gi];
+        const Tw w = stw[(1 << s) + gi];
 #pragma unroll
         for (int l = 0; l < (1 << eb); ++l) {
           const int e = (gi << (eb + 1)) | l;
@@ -543,7 +638,9 @@ __device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 of
     }
   }
   const bool final_out = !FWD && root_fold;
-  if (!FWD && MODE == kFast && !final_out) inv_pass_fixup<LOGR, R>(v, m);
+  if constexpr (!FWD && MODE == kFast) {
+    if (!final_out) inv_pass_fixup<LOGR, R>(v, m);
+  }
 #pragma unroll
   for (int e = 0; e < R; ++e)
     st_coef<ST>(result + off + ((u64)e << log_stride), final_out ? inv_out(v[e], m, out_mf) : v[e]);
@@ -555,10 +652,11 @@ __device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 of
 // log2(R) stages (inverse) on them in registers.
 template <int MODE, int LOGR, bool FWD>
 __global__ void __launch_bounds__(256)
-    ntt_col(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m, int log_n,
-            int log_s, u64 total_cols, int out_mf, int fold, Twiddle inv_n, Twiddle inv_n_w) {
+    ntt_col(u64* result, const u64* operand, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod m, int log_n,
+            int log_s, u64 total_cols, int out_mf, int fold, typename Ar<MODE>::Tw inv_n,
+            typename Ar<MODE>::Tw inv_n_w) {
   constexpr int R = 1 << LOGR;
-  __shared__ Twiddle stw[R];
+  __shared__ typename Ar<MODE>::Tw stw[R];
   const int log_cols = log_s - LOGR;                 // columns per sub-block (log2)
   const u64 g0 = (u64)blockIdx.x * blockDim.x;       // first column of this CTA
   // blockDim.x divides the columns of a sub-block, so the CTA shares one root node
@@ -591,21 +689,26 @@ __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int LOGR>
+template <int LOGR, int MODE = kGeneric>
 struct FusedCfg {
   static constexpr int LOGC = 12, C = 1 << LOGC, R = 1 << LOGR;
   static constexpr int K = R < 8 ? R : 8;            // CTAs per cluster
   static constexpr int THREADS = 256;                // = RowCfg<12>::T
-  static constexpr int MIN_BLOCKS = LOGR <= 4 ? HEXL_B200_ROW_MIN_BLOCKS : 2;
-  static constexpr size_t SMEM = RowCfg<LOGC>::ROW_BYTES;
+  static constexpr int MIN_BLOCKS = MODE == kSmall ? (LOGR <= 4 ? HEXL_B200_ROW_MIN_BLOCKS_SMALL : 3)
+                                                   : (LOGR <= 4 ? HEXL_B200_ROW_MIN_BLOCKS : 2);
+  static constexpr size_t SMEM = RowCfg<LOGC, MODE>::ROW_BYTES;
 };
 
 template <int MODE, int LOGR>
-__global__ void __launch_bounds__(FusedCfg<LOGR>::THREADS, FusedCfg<LOGR>::MIN_BLOCKS)
-    ntt_fused_fwd(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m, int out_mf) {
-  using Cfg = FusedCfg<LOGR>;
-  extern __shared__ __align__(16) u64 smem[];
-  __shared__ Twiddle stw[Cfg::R];
+__global__ void __launch_bounds__(FusedCfg<LOGR, MODE>::THREADS, FusedCfg<LOGR, MODE>::MIN_BLOCKS)
+    ntt_fused_fwd(u64* result, const u64* operand, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod m,
+                  int out_mf) {
+  using Cfg = FusedCfg<LOGR, MODE>;
+  using E = typename Ar<MODE>::E;
+  using Tw = typename Ar<MODE>::Tw;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  E* smem = reinterpret_cast<E*>(smem_raw);
+  __shared__ Tw stw[Cfg::R];
   const unsigned rank = blockIdx.x % Cfg::K;         // == %cluster_ctarank (1-D clusters)
   const u64 poly_off = (u64)(blockIdx.x / Cfg::K) << (Cfg::LOGC + LOGR);
   for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
@@ -616,7 +719,7 @@ __global__ void __launch_bounds__(FusedCfg<LOGR>::THREADS, FusedCfg<LOGR>::MIN_B
 #pragma unroll 1
   for (int c = threadIdx.x; c < COLS; c += Cfg::THREADS)
     col_body<MODE, LOGR, true, kStream, kViaL2>(result, operand, poly_off + rank * COLS + c, Cfg::LOGC, stw, m,
-                                                out_mf, false, Twiddle{}, Twiddle{});
+                                                out_mf, false, Tw{}, Tw{});
   cluster_barrier();
   // phase 2: rows rank, rank+K, ...
 #pragma unroll 1
@@ -628,12 +731,15 @@ __global__ void __launch_bounds__(FusedCfg<LOGR>::THREADS, FusedCfg<LOGR>::MIN_B
 }
 
 template <int MODE, int LOGR>
-__global__ void __launch_bounds__(FusedCfg<LOGR>::THREADS, FusedCfg<LOGR>::MIN_BLOCKS)
-    ntt_fused_inv(u64* result, const u64* operand, const Twiddle* __restrict__ tw, const Mod m, int out_mf,
-                  Twiddle inv_n, Twiddle inv_n_w) {
-  using Cfg = FusedCfg<LOGR>;
-  extern __shared__ __align__(16) u64 smem[];
-  __shared__ Twiddle stw[Cfg::R];
+__global__ void __launch_bounds__(FusedCfg<LOGR, MODE>::THREADS, FusedCfg<LOGR, MODE>::MIN_BLOCKS)
+    ntt_fused_inv(u64* result, const u64* operand, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod m,
+                  int out_mf, typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w) {
+  using Cfg = FusedCfg<LOGR, MODE>;
+  using E = typename Ar<MODE>::E;
+  using Tw = typename Ar<MODE>::Tw;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  E* smem = reinterpret_cast<E*>(smem_raw);
+  __shared__ Tw stw[Cfg::R];
   const unsigned rank = blockIdx.x % Cfg::K;
   const u64 poly_off = (u64)(blockIdx.x / Cfg::K) << (Cfg::LOGC + LOGR);
   for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
@@ -710,8 +816,26 @@ int pick_row_log(int log_n) {
 
 int pick_mode(u64 q) {
   static const bool force_generic = env_int("HEXL_B200_FORCE_GENERIC", 0) != 0;
-  return (!force_generic && q < kFastModulusLimit && q >= (1ull << 32)) ? kFast : kGeneric;
+  if (force_generic) return kGeneric;
+  if (q < kSmallModulusLimit) return kSmall;
+  return (q < kFastModulusLimit && q >= (1ull << 32)) ? kFast : kGeneric;
 }
+
+// the tables of a mode
+template <int MODE>
+struct Tab {
+  static const Twiddle* fwd(const NttDeviceTables& t) { return t.fwd; }
+  static const Twiddle* inv(const NttDeviceTables& t) { return t.inv; }
+  static Twiddle inv_n(const NttDeviceTables& t) { return t.inv_n; }
+  static Twiddle inv_n_w(const NttDeviceTables& t) { return t.inv_n_w; }
+};
+template <>
+struct Tab<kSmall> {
+  static const Twiddle32* fwd(const NttDeviceTables& t) { return t.fwd32; }
+  static const Twiddle32* inv(const NttDeviceTables& t) { return t.inv32; }
+  static Twiddle32 inv_n(const NttDeviceTables& t) { return t.inv_n32; }
+  static Twiddle32 inv_n_w(const NttDeviceTables& t) { return t.inv_n_w32; }
+};
 
 Mod make_mod(const NttDeviceTables& t) {
   Mod m;
@@ -728,7 +852,7 @@ Mod make_mod(const NttDeviceTables& t) {
 template <int MODE, int LOGC>
 cudaError_t launch_row(bool fwd, const NttDeviceTables& t, u64* result, const u64* operand,
                        u64 batch, int out_mf, int fold, cudaStream_t stream) {
-  using Cfg = RowCfg<LOGC>;
+  using Cfg = RowCfg<LOGC, MODE>;
   const unsigned rows_per_poly = (unsigned)(t.n >> LOGC);
   const u64 total_rows = batch * rows_per_poly;
   const unsigned grid = (unsigned)((total_rows + Cfg::ROWS - 1) / Cfg::ROWS);
@@ -739,8 +863,8 @@ cudaError_t launch_row(bool fwd, const NttDeviceTables& t, u64* result, const u6
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
       if (e != cudaSuccess) return e;
     }
-    ntt_row_fwd<MODE, LOGC><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, t.fwd, m, total_rows,
-                                                                       rows_per_poly, out_mf);
+    ntt_row_fwd<MODE, LOGC><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, Tab<MODE>::fwd(t), m,
+                                                                       total_rows, rows_per_poly, out_mf);
   } else {
     if (Cfg::SMEM > 48 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(ntt_row_inv<MODE, LOGC>,
@@ -748,7 +872,8 @@ cudaError_t launch_row(bool fwd, const NttDeviceTables& t, u64* result, const u6
       if (e != cudaSuccess) return e;
     }
     ntt_row_inv<MODE, LOGC><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(
-        result, operand, t.inv, m, total_rows, rows_per_poly, out_mf, fold, t.inv_n, t.inv_n_w);
+        result, operand, Tab<MODE>::inv(t), m, total_rows, rows_per_poly, out_mf, fold, Tab<MODE>::inv_n(t),
+        Tab<MODE>::inv_n_w(t));
   }
   count_launch();
   return cudaGetLastError();
@@ -777,11 +902,13 @@ cudaError_t launch_col(bool fwd, const NttDeviceTables& t, u64* result, const u6
   const unsigned grid = (unsigned)((total_cols + threads - 1) / threads);
   const Mod m = make_mod(t);
   if (fwd)
-    ntt_col<MODE, LOGR, true><<<grid, threads, 0, stream>>>(result, operand, t.fwd, m, t.log_n, log_s,
-                                                            total_cols, out_mf, fold, t.inv_n, t.inv_n_w);
+    ntt_col<MODE, LOGR, true><<<grid, threads, 0, stream>>>(result, operand, Tab<MODE>::fwd(t), m, t.log_n, log_s,
+                                                            total_cols, out_mf, fold, Tab<MODE>::inv_n(t),
+                                                            Tab<MODE>::inv_n_w(t));
   else
-    ntt_col<MODE, LOGR, false><<<grid, threads, 0, stream>>>(result, operand, t.inv, m, t.log_n, log_s,
-                                                             total_cols, out_mf, fold, t.inv_n, t.inv_n_w);
+    ntt_col<MODE, LOGR, false><<<grid, threads, 0, stream>>>(result, operand, Tab<MODE>::inv(t), m, t.log_n, log_s,
+                                                             total_cols, out_mf, fold, Tab<MODE>::inv_n(t),
+                                                             Tab<MODE>::inv_n_w(t));
   count_launch();
   return cudaGetLastError();
 }
@@ -837,7 +964,7 @@ cudaError_t simple_transform(bool fwd, const NttDeviceTables& t, u64* result, co
 template <int MODE, int LOGR>
 cudaError_t launch_fused(bool fwd, const NttDeviceTables& t, u64* result, const u64* operand, u64 batch,
                          int out_mf, cudaStream_t stream) {
-  using Cfg = FusedCfg<LOGR>;
+  using Cfg = FusedCfg<LOGR, MODE>;
   const Mod m = make_mod(t);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(batch * Cfg::K));
@@ -853,16 +980,18 @@ cudaError_t launch_fused(bool fwd, const NttDeviceTables& t, u64* result, const 
   cfg.numAttrs = 1;
   cudaError_t e;
   if (fwd)
-    e = cudaLaunchKernelEx(&cfg, ntt_fused_fwd<MODE, LOGR>, result, operand, t.fwd, m, out_mf);
+    e = cudaLaunchKernelEx(&cfg, ntt_fused_fwd<MODE, LOGR>, result, operand, Tab<MODE>::fwd(t), m, out_mf);
   else
-    e = cudaLaunchKernelEx(&cfg, ntt_fused_inv<MODE, LOGR>, result, operand, t.inv, m, out_mf, t.inv_n, t.inv_n_w);
+    e = cudaLaunchKernelEx(&cfg, ntt_fused_inv<MODE, LOGR>, result, operand, Tab<MODE>::inv(t), m, out_mf,
+                           Tab<MODE>::inv_n(t), Tab<MODE>::inv_n_w(t));
   count_launch();
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 // log2(N / 4096) for which the single fused kernel is used; 0 = none
+template <int MODE>
 int fused_log_r(int log_n) {
-  static const bool enabled = env_int("HEXL_B200_FUSED", 0) != 0;
+  static const bool enabled = MODE == kSmall ? env_int("HEXL_B200_FUSED_SMALL", 1) != 0 : env_int("HEXL_B200_FUSED", 0) != 0;
   const int lr = log_n - FusedCfg<2>::LOGC;
   return (enabled && lr >= 2 && lr <= 5) ? lr : 0;
 }
@@ -882,7 +1011,7 @@ cudaError_t launch_fused_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64*
 template <int MODE>
 cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
-  if (const int lr = fused_log_r(t.log_n)) return launch_fused_dyn<MODE>(lr, true, t, result, operand, batch, out_mf, stream);
+  if (const int lr = fused_log_r<MODE>(t.log_n)) return launch_fused_dyn<MODE>(lr, true, t, result, operand, batch, out_mf, stream);
   const int log_c = pick_row_log(t.log_n);
   int radices[8];
   const int ncol = plan_col_passes(t.log_n - log_c, radices);
@@ -900,7 +1029,7 @@ cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* opera
 template <int MODE>
 cudaError_t inverse_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
-  if (const int lr = fused_log_r(t.log_n)) return launch_fused_dyn<MODE>(lr, false, t, result, operand, batch, out_mf, stream);
+  if (const int lr = fused_log_r<MODE>(t.log_n)) return launch_fused_dyn<MODE>(lr, false, t, result, operand, batch, out_mf, stream);
   const int log_c = pick_row_log(t.log_n);
   int radices[8];
   const int ncol = plan_col_passes(t.log_n - log_c, radices);
@@ -923,16 +1052,22 @@ cudaError_t launch_ntt_forward(const NttDeviceTables& t, u64* result, const u64*
                                int /*in_mf*/, int out_mf, u64 batch, cudaStream_t stream) {
   if (batch == 0) return cudaSuccess;
   if (t.log_n < 4) return simple_transform(true, t, result, operand, out_mf, batch, stream);
-  return pick_mode(t.q) == kFast ? forward_impl<kFast>(t, result, operand, out_mf, batch, stream)
-                                 : forward_impl<kGeneric>(t, result, operand, out_mf, batch, stream);
+  switch (pick_mode(t.q)) {
+    case kFast: return forward_impl<kFast>(t, result, operand, out_mf, batch, stream);
+    case kSmall: return forward_impl<kSmall>(t, result, operand, out_mf, batch, stream);
+  }
+  return forward_impl<kGeneric>(t, result, operand, out_mf, batch, stream);
 }
 
 cudaError_t launch_ntt_inverse(const NttDeviceTables& t, u64* result, const u64* operand,
                                int /*in_mf*/, int out_mf, u64 batch, cudaStream_t stream) {
   if (batch == 0) return cudaSuccess;
   if (t.log_n < 4) return simple_transform(false, t, result, operand, out_mf, batch, stream);
-  return pick_mode(t.q) == kFast ? inverse_impl<kFast>(t, result, operand, out_mf, batch, stream)
-                                 : inverse_impl<kGeneric>(t, result, operand, out_mf, batch, stream);
+  switch (pick_mode(t.q)) {
+    case kFast: return inverse_impl<kFast>(t, result, operand, out_mf, batch, stream);
+    case kSmall: return inverse_impl<kSmall>(t, result, operand, out_mf, batch, stream);
+  }
+  return inverse_impl<kGeneric>(t, result, operand, out_mf, batch, stream);
 }
 
 }  // namespace hexl_b200

@@ -13,8 +13,9 @@ from __future__ import annotations
 import numpy as np
 
 
-def swz(j):
-    return j ^ ((j >> 4) & 15)
+def swz(j, elem_bytes=8):
+    """ntt.cu swz<E>: 64-bit elements XOR a 4-bit field, 32-bit elements (SMALL mode) a 5-bit one"""
+    return j ^ ((j >> 4) & (15 if elem_bytes == 8 else 31))
 
 
 def reg_index(u, e, lb):
@@ -100,13 +101,15 @@ class Model:
         self.cta_exchanges += 0 if max(lb_from, lb_to) <= 5 else 1
 
     @staticmethod
-    def bank_conflict_degree(u, e, lb):
-        """worst number of distinct 8-byte bank slots hit twice inside a half-warp"""
-        idx = swz(reg_index(u, e, lb))
+    def bank_conflict_degree(u, e, lb, elem_bytes=8):
+        """worst multiplicity of a 128-byte-wide bank slot inside one shared-memory wavefront:
+        a half-warp of 8-byte accesses, or a full warp of 4-byte accesses"""
+        idx = swz(reg_index(u, e, lb), elem_bytes)
+        lanes = 16 if elem_bytes == 8 else 32
         worst = 1
-        for h in range(0, len(u), 16):
-            banks = idx[h:h + 16] & 15
-            worst = max(worst, int(np.bincount(banks, minlength=16).max()))
+        for h in range(0, len(u), lanes):
+            banks = idx[h:h + lanes] & (lanes - 1)
+            worst = max(worst, int(np.bincount(banks, minlength=lanes).max()))
         return worst
 
     def row(self, data, logc, base, fwd, fold):

@@ -66,7 +66,10 @@ def test_ntt_reference_kats(hb, kats):
 # ------------------------------------------- NTT: every size against the oracle
 SIZES = [(1, 48), (2, 20), (3, 22), (4, 29), (5, 31), (6, 33), (7, 40), (8, 48), (9, 49), (10, 30),
          (10, 61), (11, 50), (12, 51), (12, 61), (13, 58), (13, 30), (14, 59), (14, 61), (15, 50), (16, 55),
-         (16, 61), (17, 60), (17, 61)]
+         (16, 61), (17, 60), (17, 61), (18, 55), (19, 61), (20, 50),  # 2^20 = the reference's maximum degree
+         # q < 2^30: the 32-bit-word kernels (GeneratePrimes(bits) returns primes just above 2^bits)
+         (4, 12), (6, 20), (8, 29), (10, 29), (11, 22), (12, 28), (13, 29), (14, 25), (15, 29), (16, 29), (17, 29),
+         (18, 29)]
 
 
 @pytest.mark.parametrize("logn,bits", SIZES)
@@ -105,12 +108,45 @@ def test_ntt_matches_oracle(hb, checker, logn, bits):
     assert (host(d) == x).all()
 
 
+def test_device_calls_capture_into_a_cuda_graph(hb, checker):
+    """Device-pointer calls only enqueue kernels on the caller's stream (no allocation,
+    no synchronisation), so a FwdNTT -> MultMod -> InvNTT product can be captured once
+    and replayed; the replayed graph is compared with the oracle on fresh inputs."""
+    n, batch = 1 << 13, 6
+    q = hb.GeneratePrimes(1, 50, True, n)[0]
+    t = hb.NTT(n, q)
+    a = torch.zeros(batch * n, dtype=torch.int64, device="cuda")
+    b = torch.zeros_like(a)
+    fa, fb, out = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+
+    def product():
+        t.ComputeForward(fa, a, 1, 4)
+        t.ComputeForward(fb, b, 1, 4)
+        hb.EltwiseMultMod(fa, fa, fb, batch * n, q, 4)
+        t.ComputeInverse(out, fa, 1, 1)
+
+    product()  # first use uploads the tables; not part of the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        product()
+    for seed in (1, 2):
+        x, y = uniform_below(seed, n * batch, q), uniform_below(seed + 10, n * batch, q)
+        a.copy_(dev(x))
+        b.copy_(dev(y))
+        g.replay()
+        torch.cuda.synchronize()
+        exp = checker.ntt_inverse(
+            checker.mult_mod(checker.ntt_forward(x, n, q), checker.ntt_forward(y, n, q), q), n, q)
+        assert (host(out) == exp).all()
+
+
 def test_ntt_extreme_inputs(hb, checker):
     """all-zero, all q-1, and lazy inputs at the top of their range (4q-1 / 2q-1), at the
     largest modulus of each arithmetic mode: q just below 2^62 (GENERIC butterflies) and
     q just below 2^56 (FAST butterflies, where the lazy ranges come closest to 2^64),
     including N = 2^17 whose column pass runs 5 unreduced stages."""
-    for bits in (61, 55):
+    for bits in (61, 55, 29):  # 29: q just below 2^30, 4q just below 2^32 (32-bit-word kernels)
         for logn in (4, 10, 12, 15, 17):
             n = 1 << logn
             q = hb.GeneratePrimes(1, bits, False, n)[0]  # largest primes below 2^(bits+1)
@@ -129,6 +165,23 @@ def test_ntt_extreme_inputs(hb, checker):
                     got = host(o)
                     assert (got % np.uint64(q) == checker.ntt_inverse(x, n, q, in_mf, 1)).all()
                     assert (got < np.uint64(2 * q)).all()
+
+
+@pytest.mark.parametrize("env", [{"HEXL_B200_FUSED": "1", "HEXL_B200_FUSED_SMALL": "1"},
+                                 {"HEXL_B200_FUSED": "0", "HEXL_B200_FUSED_SMALL": "0"},
+                                 {"HEXL_B200_FORCE_GENERIC": "1"}])
+def test_ntt_kernel_variants(env):
+    """The launch-time knobs are read once per process, so every variant (single fused
+    cluster kernel per transform, two-kernel split, GENERIC arithmetic for every modulus)
+    is checked against the oracle in its own process: tests/variant_check.py."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    res = subprocess.run([sys.executable, os.path.join(here, "variant_check.py")], env={**os.environ, **env},
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "variant ok" in res.stdout
 
 
 def test_ntt_user_root(hb, checker):

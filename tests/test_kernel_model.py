@@ -68,14 +68,24 @@ def test_col_pass_plan():
         assert sum(p) == top and max(p) <= 5
 
 
+@pytest.mark.parametrize("elem_bytes", [8, 4])
 @pytest.mark.parametrize("logc", range(8, 15))
-def test_shared_memory_maps_conflict_free(logc):
+def test_shared_memory_maps_conflict_free(logc, elem_bytes):
     u = np.arange((1 << logc) // 16)
-    lbs = {logc - 4, 0}
+    lbs = {logc - 4, 0, min(logc - 4, 4)}
     p = 1
     while logc - 4 * p - 1 >= 0:
         lbs.add(max(logc - 4 * p - 4, 0))
         p += 1
     for lb in lbs:
         for e in range(16):
-            assert Model.bank_conflict_degree(u, e, lb) == 1
+            assert Model.bank_conflict_degree(u, e, lb, elem_bytes) == 1
+
+
+@pytest.mark.parametrize("elem_bytes", [8, 4])
+def test_swizzle_is_a_bijection_inside_aligned_blocks(elem_bytes):
+    from kernel_model import swz
+    j = np.arange(1 << 14)
+    s = swz(j, elem_bytes)
+    blk = 16 if elem_bytes == 8 else 32
+    assert (np.sort(s) == j).all() and ((s // blk) == (j // blk)).all()

@@ -1,0 +1,46 @@
+"""Parity of the NTT kernels under the HEXL_B200_* launch knobs of the calling environment
+(run by tests/test_gpu_parity.py::test_ntt_kernel_variants, one process per setting)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(HERE))
+import hexl_b200 as hb  # noqa: E402
+import oracle  # noqa: E402
+from util import uniform_below  # noqa: E402
+
+checker = oracle.best_checker()
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+for logn in (12, 14, 15, 16, 17):
+    n = 1 << logn
+    for bits in (29, 50, 61):
+        q = hb.GeneratePrimes(1, bits, True, n)[0]
+        t = hb.NTT(n, q)
+        batch = 5
+        x = uniform_below(logn + bits, n * batch, q)
+        o = dev(np.zeros_like(x))
+        t.ComputeForward(o, dev(x), 1, 1)
+        assert (host(o) == checker.ntt_forward(x, n, q)).all(), ("fwd", logn, bits)
+        t.ComputeForward(o, dev(x), 1, 4)
+        g = host(o)
+        assert (g % np.uint64(q) == checker.ntt_forward(x, n, q)).all() and (g < np.uint64(4 * q)).all()
+        t.ComputeInverse(o, dev(x), 1, 1)
+        assert (host(o) == checker.ntt_inverse(x, n, q)).all(), ("inv", logn, bits)
+        d = dev(x)
+        t.ComputeForward(d, d, 1, 1)
+        t.ComputeInverse(d, d, 1, 1)
+        assert (host(d) == x).all(), ("round trip in place", logn, bits)
+print("variant ok", {k: v for k, v in os.environ.items() if k.startswith("HEXL_B200_")})

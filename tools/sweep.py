@@ -66,7 +66,7 @@ def main():
     for logn in (10, 11, 12, 13, 14, 15, 16, 17):
         n = 1 << logn
         batch = (1 << 28) // n
-        for bits in (30, 50, 55, 60):
+        for bits in (29, 50, 55, 60):
             if bits <= logn + 1:
                 continue
             q = hb.GeneratePrimes(1, bits, True, n)[0]
@@ -75,7 +75,7 @@ def main():
             y = torch.empty_like(x)
             tf = gpu_time(lambda: ntt.ComputeForward(y, x, 1, 1))
             ti = gpu_time(lambda: ntt.ComputeInverse(x, y, 1, 1))
-            mode = "FAST" if (1 << 32) <= q < (1 << 56) else "GENERIC"
+            mode = "SMALL" if q < (1 << 30) else ("FAST" if (1 << 32) <= q < (1 << 56) else "GENERIC")
             cb = max(threads * 8, 64) if logn >= 14 else max(threads * 64, 1024)
             hx = np.random.default_rng(0).integers(0, q, size=n * cb, dtype=np.uint64)
             if ref.kind == "reference":
