@@ -297,6 +297,17 @@ def run_b200_arm(args):
                 "algorithmic_bytes_per_launch": alg_bytes, "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                 "inv_achieved": alg_bytes / (inv_ms * 1e-3) / 1e9,
                 "butterflies_per_ntt": (n // 2) * args.logn}
+    # The bound that actually binds 64-bit moduli: the FMA-heavy integer pipe.
+    # A Shoup butterfly is >= 5 IMAD.WIDE + 4 IMAD = 31 pipe cycles per warp (measured issue
+    # intervals 4.6 / 2 cycles, tools/inst_bench.cu), one such pipe per SM sub-partition.
+    if q >= (1 << 30):
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        sm_hz = 1965.0e6  # max SM clock of this pool's B200s (the clocks line reports the one seen under load)
+        peak_bf = sms * 4 * 32 * sm_hz / 31.0
+        ach_bf = batch * (n // 2) * args.logn / (fwd_ms * 1e-3)
+        roofline["secondary"] = {"bound": "int-multiply pipe (IMAD/IMAD.WIDE)", "achieved": ach_bf / 1e9,
+                                 "peak": peak_bf / 1e9, "unit": "G butterflies/s", "frac": ach_bf / peak_bf,
+                                 "model": "148 SMs x 4 sub-partitions x 32 lanes x 1.965 GHz / 31 pipe cycles per warp-butterfly"}
 
     # ---- eltwise kernels (BASELINE configs[2]): algorithmic GB/s at 4096 x 2^16 elements, 60-bit q
     elt = None

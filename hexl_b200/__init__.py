@@ -69,6 +69,8 @@ _sig("hexl_b200_set_debug", None, [_int])
 _sig("hexl_b200_sync", _int, [_vp])
 _sig("hexl_b200_host_alloc", _vp, [C.c_size_t])
 _sig("hexl_b200_host_free", None, [_vp])
+_sig("hexl_b200_managed_alloc", _vp, [C.c_size_t])
+_sig("hexl_b200_managed_free", None, [_vp])
 _sig("hexl_b200_launch_count", _u64, [])
 for _n in ("multiply_mod", "add_uint_mod", "sub_uint_mod", "pow_mod", "multiply_factor"):
     _sig("hexl_b200_" + _n, _u64, [_u64, _u64, _u64])
@@ -173,6 +175,19 @@ def pinned_empty(n: int) -> np.ndarray:
 
 def pinned_free(arr: np.ndarray) -> None:
     _lib.hexl_b200_host_free(arr.ctypes.data)
+
+
+def managed_empty(n: int) -> np.ndarray:
+    """uint64 numpy array of n elements in unified memory: host code reads and writes it
+    like any array, the kernels work on it in place (no staging copy)."""
+    ptr = _lib.hexl_b200_managed_alloc(n * 8)
+    if not ptr:
+        raise HexlB200Error(-4, "hexl_b200_managed_alloc failed")
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint64)), shape=(n,))
+
+
+def managed_free(arr: np.ndarray) -> None:
+    _lib.hexl_b200_managed_free(arr.ctypes.data)
 
 
 # --------------------------------------------------------------- number theory

@@ -10,6 +10,7 @@
 //     optionally split across several GPUs with no inter-GPU traffic.
 // There is no CPU compute path here: without a CUDA device every compute entry
 // point returns HEXL_B200_ERR_NO_DEVICE.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -84,7 +85,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 enum class Where { Host, Device };
 struct PtrInfo {
   Where where;
-  int device;  // valid for Device
+  int device;            // valid for Device
+  bool managed = false;  // unified memory: the host may read it right after the call
 };
 
 int classify(const void* p, PtrInfo* out) {
@@ -97,6 +99,7 @@ int classify(const void* p, PtrInfo* out) {
   if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
     out->where = Where::Device;
     out->device = a.device;
+    out->managed = a.type == cudaMemoryTypeManaged;
   } else {
     out->where = Where::Host;
     out->device = -1;
@@ -115,9 +118,22 @@ int classify_all(std::initializer_list<const void*> ptrs, PtrInfo* out) {
     if (!have) {
       *out = pi;
       have = true;
+    } else if (pi.where == out->where && pi.where == Where::Device && pi.device == out->device) {
+      out->managed = out->managed || pi.managed;
     } else if (pi.where != out->where || (pi.where == Where::Device && pi.device != out->device)) {
       return fail(HEXL_B200_ERR_MIXED_POINTERS, "host and device pointers (or two devices) mixed in one call");
     }
+  }
+  return 0;
+}
+
+// Unified-memory buffers are what a host caller of the reference API reads back
+// immediately (hexl_b200_managed_alloc / the ManagedStrategy allocator): with no
+// explicit stream the call keeps the reference's synchronous semantics.
+int finish_device_call(const PtrInfo& pi, void* stream) {
+  if (pi.managed && stream == nullptr) {
+    cudaError_t e = cudaStreamSynchronize(nullptr);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
   }
   return 0;
 }
@@ -438,7 +454,7 @@ int ntt_compute(bool forward, hexl_b200_ntt* h, uint64_t* result, const uint64_t
     cudaError_t e = forward ? launch_ntt_forward(t, result, operand, (int)in_mf, (int)out_mf, batch, (cudaStream_t)stream)
                             : launch_ntt_inverse(t, result, operand, (int)in_mf, (int)out_mf, batch, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "NTT launch");
-    return 0;
+    return finish_device_call(pi, stream);
   }
   return run_host(result, operand, nullptr, batch * h->n, h->n, [&](int dev) {
     NttLaunch L;
@@ -482,7 +498,7 @@ int eltwise_dispatch(EltOp op, EltParams p, void* stream) {
     if (int rc = g.enter(pi.device)) return rc;
     cudaError_t e = launch_eltwise(op, p, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "eltwise launch");
-    return 0;
+    return finish_device_call(pi, stream);
   }
   return run_host(p.result, p.a, p.b, p.n, 1, [&](int) {
     EltLaunch L;
@@ -514,15 +530,42 @@ int cached_ntt(hexl_b200_ntt** out, uint64_t n, uint64_t q) {
   return 0;
 }
 
-// stream-ordered scratch memory for the composites
+// Stream-ordered scratch memory for the composites, from a pool of our own per device
+// (release threshold = keep everything: a KeySwitch re-uses the same few buffers call
+// after call; the process-wide default pool, which other libraries may tune, is left alone).
+std::mutex g_pool_mu;
+std::map<int, cudaMemPool_t> g_pools;
+int scratch_pool(cudaMemPool_t* out) {
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  auto it = g_pools.find(dev);
+  if (it == g_pools.end()) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t pool;
+    CU(cudaMemPoolCreate(&pool, &props));
+    uint64_t keep = ~0ull;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    it = g_pools.emplace(dev, pool).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
 struct Scratch {
   cudaStream_t s;
   std::vector<void*> ptrs;
   explicit Scratch(cudaStream_t st) : s(st) {}
   template <class T>
   int get(T** p, size_t count) {
+    cudaMemPool_t pool;
+    if (int rc = scratch_pool(&pool)) return rc;
     void* v = nullptr;
-    CU(cudaMallocAsync(&v, count * sizeof(T) + 16, s));
+    CU(cudaMallocFromPoolAsync(&v, count * sizeof(T) + 16, pool, s));
     ptrs.push_back(v);
     *p = static_cast<T*>(v);
     return 0;
@@ -539,15 +582,13 @@ DyadicModulus dyadic_modulus(uint64_t q) {
 
 int dyadic_on_device(uint64_t* result, const uint64_t* op1, const uint64_t* op2, uint64_t n, const uint64_t* moduli,
                      uint64_t num_moduli, cudaStream_t s) {
-  std::vector<DyadicModulus> mods(num_moduli);
-  for (uint64_t i = 0; i < num_moduli; ++i) mods[i] = dyadic_modulus(moduli[i]);
-  Scratch ws(s);
-  DyadicModulus* d_mods = nullptr;
-  if (int rc = ws.get(&d_mods, num_moduli)) return rc;
-  CU(cudaMemcpyAsync(d_mods, mods.data(), num_moduli * sizeof(DyadicModulus), cudaMemcpyHostToDevice, s));
-  cudaError_t e = launch_dyadic_multiply(result, op1, op2, n, num_moduli, d_mods, s);
-  if (e != cudaSuccess) return cuda_fail(e, "DyadicMultiply launch");
-  CU(cudaStreamSynchronize(s));  // `mods` is pageable host memory feeding an async copy
+  for (uint64_t first = 0; first < num_moduli; first += kParamBlock) {
+    const uint64_t count = std::min<uint64_t>(kParamBlock, num_moduli - first);
+    DyadicModuli mods;
+    for (uint64_t i = 0; i < count; ++i) mods.m[i] = dyadic_modulus(moduli[first + i]);
+    cudaError_t e = launch_dyadic_multiply(result, op1, op2, n, num_moduli, first, count, mods, s);
+    if (e != cudaSuccess) return cuda_fail(e, "DyadicMultiply launch");
+  }
   return 0;
 }
 
@@ -571,13 +612,10 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
   }
   Scratch ws(s);
   uint64_t *t_coef = nullptr, *ops = nullptr, *prod = nullptr, *tmp = nullptr;
-  const uint64_t** d_keys = nullptr;
   if (int rc = ws.get(&t_coef, decomp * n)) return rc;
   if (int rc = ws.get(&ops, decomp * n)) return rc;
   if (int rc = ws.get(&prod, kcc * rns * n)) return rc;
   if (int rc = ws.get(&tmp, decomp * kcc * n)) return rc;
-  if (int rc = ws.get(&d_keys, decomp)) return rc;
-  CU(cudaMemcpyAsync(d_keys, d_key_ptrs_host, decomp * sizeof(uint64_t*), cudaMemcpyHostToDevice, s));
 #define LAUNCH(expr)                                                    \
   do {                                                                  \
     cudaError_t e__ = (expr);                                           \
@@ -606,7 +644,13 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
     }
     const uint64_t r64 = nt::multiply_factor(1, 64, q) * (0 - q) /* 2^64 - floor(2^64/q)*q = 2^64 mod q */;
     const Twiddle R = make_twiddle(r64 % q, q);
-    LAUNCH(launch_ks_mac(prod + i * n, ops, d_keys, n, decomp, kcc, ki, key_modulus_size, rns * n, q, mu, R, s));
+    for (uint64_t j0 = 0; j0 < decomp; j0 += kParamBlock) {  // key pointers ride in the kernel parameters
+      const uint64_t cnt = std::min<uint64_t>(kParamBlock, decomp - j0);
+      KeyPointers kp;
+      for (uint64_t j = 0; j < cnt; ++j) kp.p[j] = d_key_ptrs_host[j0 + j];
+      LAUNCH(launch_ks_mac(prod + i * n, ops + j0 * n, kp, n, cnt, kcc, ki, key_modulus_size, rns * n, q, mu, R,
+                           j0 != 0, s));
+    }
   }
   // 3. mod-down by the special prime and accumulate into result (:134-198)
   const uint64_t q_last = moduli[key_modulus_size - 1], mu_last = nt::multiply_factor(1, 64, q_last);
@@ -628,8 +672,7 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
                               ms.w, ms.wp, s));
   }
 #undef LAUNCH
-  CU(cudaStreamSynchronize(s));  // scratch and the pointer table are released by ~Scratch after this
-  return 0;
+  return 0;  // asynchronous on s; ~Scratch returns the buffers to the pool in stream order
 }
 
 int debug_bounds(const u64* p, u64 n, u64 bound, const char* what, std::initializer_list<const void*> all) {
@@ -686,6 +729,17 @@ void* hexl_b200_host_alloc(size_t bytes) {
 }
 void hexl_b200_host_free(void* p) {
   if (p) cudaFreeHost(p);
+}
+void* hexl_b200_managed_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocManaged(&p, bytes ? bytes : 1, cudaMemAttachGlobal) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void hexl_b200_managed_free(void* p) {
+  if (p) cudaFree(p);
 }
 
 uint64_t hexl_b200_launch_count(void) { return launches_so_far(); }
@@ -930,7 +984,8 @@ int hexl_b200_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const 
   if (pi.where == Where::Device) {
     DeviceGuard g;
     if (int rc = g.enter(pi.device)) return rc;
-    return dyadic_on_device(result, operand1, operand2, n, moduli, num_moduli, (cudaStream_t)stream);
+    if (int rc = dyadic_on_device(result, operand1, operand2, n, moduli, num_moduli, (cudaStream_t)stream)) return rc;
+    return finish_device_call(pi, stream);
   }
   int cur = 0;
   CU(cudaGetDevice(&cur));
@@ -966,8 +1021,10 @@ int hexl_b200_key_switch(uint64_t* result, const uint64_t* t_target_iter_ptr, ui
   if (pi.where == Where::Device) {
     DeviceGuard g;
     if (int rc = g.enter(pi.device)) return rc;
-    return key_switch_on_device(pi.device, result, t_target_iter_ptr, n, decomp, key_modulus_size, rns, kcc, moduli,
-                                k_switch_keys, modswitch_factors, (cudaStream_t)stream);
+    if (int rc = key_switch_on_device(pi.device, result, t_target_iter_ptr, n, decomp, key_modulus_size, rns, kcc,
+                                      moduli, k_switch_keys, modswitch_factors, (cudaStream_t)stream))
+      return rc;
+    return finish_device_call(pi, stream);
   }
   int cur = 0;
   CU(cudaGetDevice(&cur));

@@ -63,11 +63,22 @@ struct DyadicModulus {  // per RNS modulus: q and its generalised-Barrett consta
   u64 q, mu;
   int shift;
 };
-cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli,
-                                   const DyadicModulus* d_mods, cudaStream_t stream);
-cudaError_t launch_ks_mac(u64* prod_i, const u64* operands, const u64* const* d_keys, u64 n, u64 decomp, u64 kcc,
+// Small per-call tables travel as kernel parameters (no upload, no synchronisation, capturable
+// in a CUDA graph); longer lists are processed in blocks of this many entries.
+constexpr int kParamBlock = 64;
+struct DyadicModuli {
+  DyadicModulus m[kParamBlock];
+};
+struct KeyPointers {
+  const u64* p[kParamBlock];
+};
+// moduli [first, first + count) of a DyadicMultiply over `num_moduli` moduli
+cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli, u64 first,
+                                   u64 count, const DyadicModuli& mods, cudaStream_t stream);
+// digits [0, count) of `keys`/`operands`; accumulate != 0 adds to the value already in prod_i (mod q)
+cudaError_t launch_ks_mac(u64* prod_i, const u64* operands, const KeyPointers& keys, u64 n, u64 count, u64 kcc,
                           u64 key_index, u64 key_modulus_size, u64 prod_stride_k, u64 q, u64 mu, Twiddle r64,
-                          cudaStream_t stream);
+                          int accumulate, cudaStream_t stream);
 cudaError_t launch_ks_round(u64* out, const u64* t_last, u64 n, u64 q_last, u64 mu_last, u64 q_i, u64 mu_i, u64 fix,
                             cudaStream_t stream);
 cudaError_t launch_ks_finish(u64* result, const u64* prod, const u64* t_ntt, u64 n, u64 q, u64 ms, u64 ms_p,

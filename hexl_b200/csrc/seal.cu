@@ -28,12 +28,14 @@ __device__ __forceinline__ u64 mulmod(u64 x, u64 y, const MulCtx& c) {
 // coalesced; inputs are read before any output is written, so result may alias
 // either operand (test-dyadic-multiply.cpp:38-112).
 __global__ void __launch_bounds__(kThreads)
-    dyadic_kernel(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli, const DyadicModulus* mods) {
-  const u64 total = n * num_moduli, poly = total;
+    dyadic_kernel(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli, u64 first, u64 count,
+                  const __grid_constant__ DyadicModuli mods) {
+  const u64 total = n * count, poly = n * num_moduli, base = first * n;
   const u64 stride = (u64)gridDim.x * kThreads;
-  for (u64 o = (u64)blockIdx.x * kThreads + threadIdx.x; o < total; o += stride) {
-    const DyadicModulus dm = mods[o / n];
+  for (u64 i = (u64)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
+    const DyadicModulus& dm = mods.m[i / n];
     const MulCtx c{dm.q, dm.mu, dm.shift};
+    const u64 o = base + i;
     const u64 x0 = __ldcs(op1 + o), x1 = __ldcs(op1 + o + poly);
     const u64 y0 = __ldcs(op2 + o), y1 = __ldcs(op2 + o + poly);
     const u64 r0 = mulmod(x0, y0, c);
@@ -52,25 +54,27 @@ __global__ void __launch_bounds__(kThreads)
 // and stores acc mod q.  acc = hi*2^64 + lo is reduced as
 // Shoup(hi, 2^64 mod q) + Barrett(lo), both lazy, then two conditional subtractions.
 __global__ void __launch_bounds__(kThreads)
-    ks_mac_kernel(u64* prod_i /* [kcc][rns*n] slice base + i*n */, const u64* operands /* [decomp][n] */,
-                  const u64* const* keys /* device array of decomp pointers */, u64 n, u64 decomp, u64 kcc,
-                  u64 key_index, u64 key_modulus_size, u64 prod_stride_k, u64 q, u64 mu, Twiddle r64) {
+    ks_mac_kernel(u64* prod_i /* [kcc][rns*n] slice base + i*n */, const u64* operands /* [count][n] */,
+                  const __grid_constant__ KeyPointers keys, u64 n, u64 count, u64 kcc, u64 key_index,
+                  u64 key_modulus_size, u64 prod_stride_k, u64 q, u64 mu, Twiddle r64, int accumulate) {
   const u64 total = kcc * n;
   const u64 g = (u64)blockIdx.x * kThreads + threadIdx.x;
   if (g >= total) return;
   const u64 k = g / n, l = g - k * n;
   const u64 key_off = n * key_index + k * key_modulus_size * n + l;
   u64 lo = 0, hi = 0;
-  for (u64 j = 0; j < decomp; ++j) {
+  for (u64 j = 0; j < count; ++j) {
     const u64 a = operands[j * n + l];
-    const u64 b = __ldcs(keys[j] + key_off);
+    const u64 b = __ldcs(keys.p[j] + key_off);
     const u64 plo = a * b, phi = mulhi(a, b);
     lo += plo;
     hi += phi + (lo < plo);
   }
   u64 r = shoup_lazy(hi, r64.w, r64.wp, q) + barrett64_lazy(lo, q, mu);  // < 4q
   r = csub(csub(r, q << 1), q);
-  prod_i[k * prod_stride_k + l] = r;
+  u64* dst = prod_i + k * prod_stride_k + l;
+  if (accumulate) r = csub(r + *dst, q);
+  *dst = r;
 }
 
 // ---- KeySwitch tail, first half (key-switch-internal.cpp:148-178): the special
@@ -103,25 +107,25 @@ unsigned blocks_for(u64 items) { return (unsigned)((items + kThreads - 1) / kThr
 
 }  // namespace
 
-cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli,
-                                   const DyadicModulus* d_mods, cudaStream_t stream) {
-  const u64 total = n * num_moduli;
+cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli, u64 first,
+                                   u64 count, const DyadicModuli& mods, cudaStream_t stream) {
+  const u64 total = n * count;
   if (total == 0) return cudaSuccess;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   u64 blocks = blocks_for(total);
   if (blocks > (u64)sms * 8) blocks = (u64)sms * 8;
-  dyadic_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(result, op1, op2, n, num_moduli, d_mods);
+  dyadic_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(result, op1, op2, n, num_moduli, first, count, mods);
   count_launch();
   return cudaGetLastError();
 }
 
-cudaError_t launch_ks_mac(u64* prod_i, const u64* operands, const u64* const* d_keys, u64 n, u64 decomp, u64 kcc,
+cudaError_t launch_ks_mac(u64* prod_i, const u64* operands, const KeyPointers& keys, u64 n, u64 count, u64 kcc,
                           u64 key_index, u64 key_modulus_size, u64 prod_stride_k, u64 q, u64 mu, Twiddle r64,
-                          cudaStream_t stream) {
-  ks_mac_kernel<<<blocks_for(kcc * n), kThreads, 0, stream>>>(prod_i, operands, d_keys, n, decomp, kcc, key_index,
-                                                             key_modulus_size, prod_stride_k, q, mu, r64);
+                          int accumulate, cudaStream_t stream) {
+  ks_mac_kernel<<<blocks_for(kcc * n), kThreads, 0, stream>>>(prod_i, operands, keys, n, count, kcc, key_index,
+                                                             key_modulus_size, prod_stride_k, q, mu, r64, accumulate);
   count_launch();
   return cudaGetLastError();
 }

@@ -104,6 +104,22 @@ struct MallocStrategy : AllocatorBase {
 
 using AllocatorStrategyPtr = std::shared_ptr<AllocatorBase>;
 
+// GPU-aware strategies for the same hook (not in the reference).  Buffers of an
+// AlignedVector64 built on PinnedStrategy stream over PCIe at full rate through the
+// host-pointer path; buffers built on ManagedStrategy are unified memory and are
+// worked on in place by the kernels, no staging copy at all:
+//   AlignedVector64<uint64_t> v(n, 0, AlignedAllocator<uint64_t, 64>(std::make_shared<b200::ManagedStrategy>()));
+namespace b200 {
+struct PinnedStrategy : AllocatorBase {
+  void* allocate(size_t bytes_count) final { return hexl_b200_host_alloc(bytes_count); }
+  void deallocate(void* p, size_t) final { hexl_b200_host_free(p); }
+};
+struct ManagedStrategy : AllocatorBase {
+  void* allocate(size_t bytes_count) final { return hexl_b200_managed_alloc(bytes_count); }
+  void deallocate(void* p, size_t) final { hexl_b200_managed_free(p); }
+};
+}  // namespace b200
+
 inline AllocatorStrategyPtr& DefaultMallocStrategy() {
   static AllocatorStrategyPtr s = AllocatorStrategyPtr(new MallocStrategy);
   return s;

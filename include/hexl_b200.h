@@ -66,6 +66,12 @@ int hexl_b200_sync(void* stream);
  * is the place a caller would plug these in). */
 void* hexl_b200_host_alloc(size_t bytes);
 void hexl_b200_host_free(void* p);
+/* Unified (managed) memory: one pointer valid on the host and on every GPU, so a
+ * caller's buffers are device-visible with no staging copy.  Calls on managed
+ * buffers with stream == NULL return after the result is complete (the
+ * reference's synchronous semantics); with a stream they are asynchronous. */
+void* hexl_b200_managed_alloc(size_t bytes);
+void hexl_b200_managed_free(void* p);
 /* number of kernel launches this library has issued in this process */
 uint64_t hexl_b200_launch_count(void);
 

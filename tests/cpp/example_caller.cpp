@@ -115,6 +115,32 @@ int main(int argc, char** argv) {
       ntt.ComputeForward(out.data(), in.data(), 1, 1);
       Expect(out, want, "NTT N=32 known answer");
     }
+    {
+      // the same known answer on AlignedVector64 buffers whose storage comes from the
+      // GPU-aware allocator strategies: unified memory (worked on in place, read back by
+      // the host right after the call) and pinned host memory (staged at full PCIe rate)
+      const uint64_t in[32] = {401, 203, 221, 352, 487, 151, 405, 356, 343, 424, 635, 757, 457, 280, 624, 353,
+                               496, 353, 624, 280, 457, 757, 635, 424, 343, 356, 405, 151, 487, 352, 221, 203};
+      NTT ntt(32, 769);
+      AllocatorStrategyPtr strategies[2] = {std::make_shared<b200::ManagedStrategy>(),
+                                            std::make_shared<b200::PinnedStrategy>()};
+      for (auto& strat : strategies) {
+        AlignedVector64<uint64_t> v(in, in + 32, AlignedAllocator<uint64_t, 64>(strat));
+        ntt.ComputeForward(v.data(), v.data(), 1, 1);
+        for (int i = 0; i < 32; ++i)
+          if (v[i] != uint64_t(i + 1)) {
+            std::printf("allocator-strategy buffer: forward[%d] = %llu\n", i, (unsigned long long)v[i]);
+            ++failures;
+            break;
+          }
+        ntt.ComputeInverse(v.data(), v.data(), 1, 1);
+        for (int i = 0; i < 32; ++i)
+          if (v[i] != in[i]) {
+            ++failures;
+            break;
+          }
+      }
+    }
     bool threw = false;
     try {
       std::vector<uint64_t> a{1, 2};

@@ -184,6 +184,28 @@ def test_ntt_kernel_variants(env):
     assert "variant ok" in res.stdout
 
 
+def test_unified_memory_buffers(hb, checker):
+    """hexl_b200_managed_alloc: the host fills and reads the buffers directly, the kernels
+    work on them in place, and a call without a stream returns with the result complete."""
+    n, batch = 1 << 12, 3
+    q = hb.GeneratePrimes(1, 55, True, n)[0]
+    t = hb.NTT(n, q)
+    a, b, r = hb.managed_empty(n * batch), hb.managed_empty(n * batch), hb.managed_empty(n * batch)
+    try:
+        x, y = uniform_below(5, n * batch, q), uniform_below(6, n * batch, q)
+        a[:] = x
+        b[:] = y
+        t.ComputeForward(r, a, 1, 1)
+        assert (r == checker.ntt_forward(x, n, q)).all()
+        hb.EltwiseMultMod(r, a, b, n * batch, q, 1)
+        assert (r == checker.mult_mod(x, y, q)).all()
+        t.ComputeInverse(a, a, 1, 1)  # in place
+        assert (a == checker.ntt_inverse(x, n, q)).all()
+    finally:
+        for arr in (a, b, r):
+            hb.managed_free(arr)
+
+
 def test_ntt_user_root(hb, checker):
     n = 256
     q = hb.GeneratePrimes(1, 40, True, n)[0]
@@ -487,7 +509,7 @@ def test_key_switch_reference_kat(hb):
     assert (host(dres) == exp).all()
 
 
-@pytest.mark.parametrize("logn,decomp,bits", [(12, 3, 50), (13, 4, 58), (15, 6, 50)])
+@pytest.mark.parametrize("logn,decomp,bits", [(12, 3, 50), (13, 4, 58), (15, 6, 50), (10, 67, 40)])  # 67 > one parameter block
 def test_key_switch_matches_oracle(hb, checker, logn, decomp, bits):
     """CKKS key-switch shape of BASELINE config 5 (N = 2^15, many RNS moduli) against the
     compiled reference / oracle on random data."""
@@ -504,6 +526,51 @@ def test_key_switch_matches_oracle(hb, checker, logn, decomp, bits):
     dres = dev(result)
     hb.KeySwitch(dres, dev(t_target), n, decomp, kms, rns, kcc, mods, [dev(x) for x in keys], modswitch)
     assert (host(dres) == exp).all()
+
+
+def test_dyadic_multiply_many_moduli(hb, checker):
+    """more moduli than one kernel-parameter block (64)"""
+    n = 256
+    mods = hb.GeneratePrimes(70, 45, True, n)
+    a = np.concatenate([uniform_below(10 + i, n, q) for _ in range(2) for i, q in enumerate(mods)])
+    b = np.concatenate([uniform_below(200 + i, n, q) for _ in range(2) for i, q in enumerate(mods)])
+    out = torch.zeros(3 * n * len(mods), dtype=torch.int64, device="cuda")
+    hb.DyadicMultiply(out, dev(a), dev(b), n, mods)
+    assert (host(out) == checker.dyadic_multiply(a, b, n, mods)).all()
+
+
+def test_key_switch_is_asynchronous_and_graph_capturable(hb, checker):
+    """A device-pointer KeySwitch only enqueues work on the caller's stream (scratch comes
+    from a stream-ordered pool, small tables ride in kernel parameters): it can be captured
+    into a CUDA graph and replayed on new data."""
+    n, decomp, kcc = 1 << 12, 4, 2
+    kms = rns = decomp + 1
+    mods = hb.GeneratePrimes(kms, 50, True, n)
+    modswitch = [hb.InverseMod(mods[-1] % mods[i], mods[i]) for i in range(decomp)]
+    keys = [np.concatenate([uniform_below(100 * j + 7 * k + i, n, mods[i]) for k in range(kcc) for i in range(kms)])
+            for j in range(decomp)]
+    dkeys = [dev(x) for x in keys]
+    dt = torch.zeros(decomp * n, dtype=torch.int64, device="cuda")
+    dres = torch.zeros(kcc * decomp * n, dtype=torch.int64, device="cuda")
+
+    def call():
+        hb.KeySwitch(dres, dt, n, decomp, kms, rns, kcc, mods, dkeys, modswitch)
+
+    call()  # tables, pool and function attributes are set up outside the capture
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        call()
+    for seed in (3, 4):
+        t_target = np.concatenate([uniform_below(seed * 50 + j, n, mods[j]) for j in range(decomp)])
+        result = np.concatenate([uniform_below(seed * 500 + 10 * k + i, n, mods[i])
+                                 for k in range(kcc) for i in range(decomp)])
+        dt.copy_(dev(t_target))
+        dres.copy_(dev(result))
+        g.replay()
+        torch.cuda.synchronize()
+        exp = checker.key_switch(result.copy(), t_target, n, decomp, kms, rns, kcc, mods, keys, modswitch)
+        assert (host(dres) == exp).all()
 
 
 def test_ntt_cache(hb):
