@@ -92,6 +92,8 @@ _sig("hexl_b200_ntt_minimal_root", _u64, [_vp])
 _sig("hexl_b200_ntt_table", C.POINTER(_u64), [_vp, _int])
 _sig("hexl_b200_ntt_forward", _int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_ntt_inverse", _int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp])
+_sig("hexl_b200_ntt_forward_multi", _int, [C.POINTER(_vp), _u64, _vp, _vp, _u64, _u64, _u64, _vp])
+_sig("hexl_b200_ntt_inverse_multi", _int, [C.POINTER(_vp), _u64, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_eltwise_add_mod", _int, [_vp, _vp, _vp, _u64, _u64, _vp])
 _sig("hexl_b200_eltwise_add_mod_scalar", _int, [_vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_eltwise_sub_mod", _int, [_vp, _vp, _vp, _u64, _u64, _vp])
@@ -262,6 +264,33 @@ class NTT:
     def ComputeInverse(self, result, operand, input_mod_factor=1, output_mod_factor=1, stream=None):
         return self._compute(_lib.hexl_b200_ntt_inverse, result, operand, input_mod_factor,
                              output_mod_factor, stream)
+
+
+def _multi(fn, ntts, result, operand, in_mf, out_mf, batch_per_modulus, stream):
+    rp, rn, rc = _buf(result)
+    op, on, oc = _buf(operand)
+    n = ntts[0].GetDegree()
+    if batch_per_modulus is None:
+        assert on % (n * len(ntts)) == 0, "operand length must be a multiple of len(ntts) * degree"
+        batch_per_modulus = on // (n * len(ntts))
+    assert rn >= batch_per_modulus * n * len(ntts) and on >= batch_per_modulus * n * len(ntts)
+    hs = (_vp * len(ntts))(*[t._h for t in ntts])
+    _check(fn(hs, len(ntts), rp, op, in_mf, out_mf, batch_per_modulus, _stream(stream, rc or oc)))
+    return result
+
+
+def ComputeForwardMulti(ntts, result, operand, input_mod_factor=1, output_mod_factor=1, batch_per_modulus=None,
+                        stream=None):
+    """One launch for an RNS batch: polynomial u is transformed under ntts[u // batch_per_modulus]
+    (hexl_b200_ntt_forward_multi; the reference needs one NTT::ComputeForward call per unit)."""
+    return _multi(_lib.hexl_b200_ntt_forward_multi, ntts, result, operand, input_mod_factor, output_mod_factor,
+                  batch_per_modulus, stream)
+
+
+def ComputeInverseMulti(ntts, result, operand, input_mod_factor=1, output_mod_factor=1, batch_per_modulus=None,
+                        stream=None):
+    return _multi(_lib.hexl_b200_ntt_inverse_multi, ntts, result, operand, input_mod_factor, output_mod_factor,
+                  batch_per_modulus, stream)
 
 
 # ---------------------------------------------------------------- element-wise

@@ -25,8 +25,8 @@ OBJ = os.path.join(PKG, "_obj" + SUFFIX)
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, f"libhexl_b200{SUFFIX}.so")
 
-SOURCES = ["capi.cu", "ntt.cu", "eltwise.cu", "seal.cu", "numtheory.cpp"]
-HEADERS = ["internal.h", "modarith.cuh", "numtheory.h", os.path.join(ROOT, "include", "hexl_b200.h")]
+SOURCES = ["capi.cu", "ntt.cu", "ntt_multi.cu", "eltwise.cu", "seal.cu", "numtheory.cpp"]
+HEADERS = ["internal.h", "modarith.cuh", "ntt_kernels.cuh", "numtheory.h", os.path.join(ROOT, "include", "hexl_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

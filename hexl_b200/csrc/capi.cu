@@ -48,6 +48,7 @@ struct hexl_b200_ntt {
     Twiddle* inv = nullptr;
     Twiddle32* fwd32 = nullptr;  // q < 2^30 only
     Twiddle32* inv32 = nullptr;
+    NttDeviceParams* params = nullptr;
   };
   std::map<int, Dev> dev;  // device ordinal -> uploaded tables
 };
@@ -374,8 +375,12 @@ int device_tables(hexl_b200_ntt* h, int dev, NttDeviceTables* out) {
       CU(cudaMemcpy(d.fwd32, f32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
       CU(cudaMemcpy(d.inv32, i32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
     }
+    NttDeviceParams hp{d.fwd, d.inv, h->q, nt::multiply_factor(1, 64, h->q), h->inv_n, h->inv_n_w};
+    CU(cudaMalloc(&d.params, sizeof(NttDeviceParams)));
+    CU(cudaMemcpy(d.params, &hp, sizeof(NttDeviceParams), cudaMemcpyHostToDevice));
     it = h->dev.emplace(dev, d).first;
   }
+  out->dparams = it->second.params;
   out->fwd = it->second.fwd;
   out->inv = it->second.inv;
   out->fwd32 = it->second.fwd32;
@@ -592,13 +597,17 @@ int dyadic_on_device(uint64_t* result, const uint64_t* op1, const uint64_t* op2,
   return 0;
 }
 
-// key-switch-internal.cpp:25-201 as a stream-ordered chain of kernels; every
-// pointer is a device pointer on the current device.
+int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
+                        const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s);
+
+// key-switch-internal.cpp:25-201 as a short chain of launches on the caller's stream, every
+// step batched over the RNS moduli (multi-modulus NTTs + the glue kernels of seal.cu): about a
+// dozen launches whatever the number of moduli, instead of ~10 per modulus.  Every pointer is
+// a device pointer on the current device.  Scratch layouts are [modulus][digit or component][n].
 int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, uint64_t n, uint64_t decomp,
                          uint64_t key_modulus_size, uint64_t rns, uint64_t kcc, const uint64_t* moduli,
                          const uint64_t* const* d_key_ptrs_host, const uint64_t* modswitch, cudaStream_t s) {
   std::vector<hexl_b200_ntt*> h(key_modulus_size, nullptr);
-  std::vector<NttDeviceTables> tab(key_modulus_size);
   struct Release {
     std::vector<hexl_b200_ntt*>& v;
     ~Release() {
@@ -606,73 +615,133 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
         if (p) hexl_b200_ntt_release(p);
     }
   } release{h};
-  for (uint64_t i = 0; i < key_modulus_size; ++i) {
+  for (uint64_t i = 0; i < key_modulus_size; ++i)
     if (int rc = cached_ntt(&h[i], n, moduli[i])) return rc;
-    if (int rc = device_tables(h[i], dev, &tab[i])) return rc;
-  }
+  // RNS modulus i of the computation lives in slot ki(i) of the key / moduli arrays (:62-63)
+  auto ki = [&](uint64_t i) { return i == decomp ? key_modulus_size - 1 : i; };
+  // moduli handled per round of step 2: bounded by the parameter block and by ~256 MiB of scratch
+  const uint64_t per_mod = decomp * n;
+  uint64_t ichunk = std::max<uint64_t>(1, (256ull << 20) / (per_mod * 8));
+  ichunk = std::min<uint64_t>({ichunk, rns, (uint64_t)kParamBlock});
   Scratch ws(s);
   uint64_t *t_coef = nullptr, *ops = nullptr, *prod = nullptr, *tmp = nullptr;
-  if (int rc = ws.get(&t_coef, decomp * n)) return rc;
-  if (int rc = ws.get(&ops, decomp * n)) return rc;
-  if (int rc = ws.get(&prod, kcc * rns * n)) return rc;
-  if (int rc = ws.get(&tmp, decomp * kcc * n)) return rc;
+  if (int rc = ws.get(&t_coef, per_mod)) return rc;
+  if (int rc = ws.get(&ops, ichunk * per_mod)) return rc;
+  if (int rc = ws.get(&prod, rns * kcc * n)) return rc;   // [i][k][n]
+  if (int rc = ws.get(&tmp, decomp * kcc * n)) return rc;  // [i][k][n]
 #define LAUNCH(expr)                                                    \
   do {                                                                  \
     cudaError_t e__ = (expr);                                           \
     if (e__ != cudaSuccess) return cuda_fail(e__, "KeySwitch: " #expr); \
   } while (0)
-  // 1. digits back to coefficient form (:49-55)
-  for (uint64_t j = 0; j < decomp; ++j)
-    LAUNCH(launch_ntt_inverse(tab[j], t_coef + j * n, t_target + j * n, 2, 1, 1, s));
-  // 2. per RNS modulus: convert every other digit, multiply-accumulate with the keys (:60-131)
-  for (uint64_t i = 0; i < rns; ++i) {
-    const uint64_t ki = (i == decomp) ? key_modulus_size - 1 : i;
-    const uint64_t q = moduli[ki], mu = nt::multiply_factor(1, 64, q);
-    // x mod q for every digit: the reference copies when q_j <= q (then x < q already) and
-    // reduces otherwise (:77-85); one Barrett pass over all digits does both
-    EltParams rp{};
-    rp.result = ops; rp.a = t_coef; rp.n = decomp * n; rp.q = q; rp.mu = mu; rp.in_mf = 0; rp.out_mf = 1;
-    LAUNCH(launch_eltwise(EltOp::Reduce, rp, s));
-    if (i > 0 || i == decomp) {
-      const uint64_t cnt = (i < decomp) ? i : decomp;
-      if (cnt) LAUNCH(launch_ntt_forward(tab[ki], ops, ops, 4, 4, cnt, s));
+  // 1. digits back to coefficient form, each under its own modulus (:49-55)
+  if (int rc = ntt_multi_on_device(false, dev, h.data(), decomp, t_coef, t_target, 1, 1, s)) return rc;
+  // 2. every digit under every modulus: reduce, lazy forward NTT, multiply-accumulate with the keys (:60-131).
+  //    (The digit that already lives in modulus i is re-derived like the others: NTT(INTT(x)) = x mod q_i.)
+  for (uint64_t i0 = 0; i0 < rns; i0 += ichunk) {
+    const uint64_t cnt = std::min(ichunk, rns - i0);
+    KsModuli mods;
+    std::vector<hexl_b200_ntt*> hs(cnt);
+    for (uint64_t e = 0; e < cnt; ++e) {
+      const uint64_t slot = ki(i0 + e), q = moduli[slot], mu = nt::multiply_factor(1, 64, q);
+      const uint64_t r64 = mu * (0 - q);  // 2^64 - floor(2^64/q)*q = 2^64 mod q
+      const Twiddle R = make_twiddle(r64 % q, q);
+      mods.m[e] = KsModulus{q, mu, R.w, R.wp, slot};
+      hs[e] = h[slot];
     }
-    if (i < decomp) {
-      if (i + 1 < decomp)
-        LAUNCH(launch_ntt_forward(tab[ki], ops + (i + 1) * n, ops + (i + 1) * n, 4, 4, decomp - i - 1, s));
-      CU(cudaMemcpyAsync(ops + i * n, t_target + i * n, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, s));
-    }
-    const uint64_t r64 = nt::multiply_factor(1, 64, q) * (0 - q) /* 2^64 - floor(2^64/q)*q = 2^64 mod q */;
-    const Twiddle R = make_twiddle(r64 % q, q);
+    LAUNCH(launch_ks_reduce(ops, t_coef, n, decomp, cnt, mods, s));
+    if (int rc = ntt_multi_on_device(true, dev, hs.data(), cnt, ops, ops, 4, decomp, s)) return rc;
     for (uint64_t j0 = 0; j0 < decomp; j0 += kParamBlock) {  // key pointers ride in the kernel parameters
-      const uint64_t cnt = std::min<uint64_t>(kParamBlock, decomp - j0);
+      const uint64_t jc = std::min<uint64_t>(kParamBlock, decomp - j0);
       KeyPointers kp;
-      for (uint64_t j = 0; j < cnt; ++j) kp.p[j] = d_key_ptrs_host[j0 + j];
-      LAUNCH(launch_ks_mac(prod + i * n, ops + j0 * n, kp, n, cnt, kcc, ki, key_modulus_size, rns * n, q, mu, R,
+      for (uint64_t j = 0; j < jc; ++j) kp.p[j] = d_key_ptrs_host[j0 + j];
+      LAUNCH(launch_ks_mac(prod + i0 * kcc * n, ops + j0 * n, per_mod, kp, n, jc, kcc, key_modulus_size, cnt, mods,
                            j0 != 0, s));
     }
   }
   // 3. mod-down by the special prime and accumulate into result (:134-198)
   const uint64_t q_last = moduli[key_modulus_size - 1], mu_last = nt::multiply_factor(1, 64, q_last);
-  for (uint64_t k = 0; k < kcc; ++k) {
-    uint64_t* t_last = prod + k * rns * n + decomp * n;
-    LAUNCH(launch_ntt_inverse(tab[key_modulus_size - 1], t_last, t_last, 2, 2, 1, s));
-    for (uint64_t i = 0; i < decomp; ++i) {
-      const uint64_t qi = moduli[i], mu_i = nt::multiply_factor(1, 64, qi);
-      const uint64_t fix = qi - ((q_last >> 1) % qi);
-      LAUNCH(launch_ks_round(tmp + (i * kcc + k) * n, t_last, n, q_last, mu_last, qi, mu_i, fix, s));
-    }
+  uint64_t* t_last = prod + decomp * kcc * n;  // [k][n], contiguous
+  {
+    NttDeviceTables tl;
+    if (int rc = device_tables(h[key_modulus_size - 1], dev, &tl)) return rc;
+    LAUNCH(launch_ntt_inverse(tl, t_last, t_last, 2, 2, kcc, s));
   }
-  for (uint64_t i = 0; i < decomp; ++i) {
-    const uint64_t qi = moduli[i];
-    LAUNCH(launch_ntt_forward(tab[i], tmp + i * kcc * n, tmp + i * kcc * n, 4, 4, kcc, s));
-    const Twiddle ms = make_twiddle(modswitch[i] % qi, qi);
-    for (uint64_t k = 0; k < kcc; ++k)
-      LAUNCH(launch_ks_finish(result + n * (decomp * k + i), prod + k * rns * n + i * n, tmp + (i * kcc + k) * n, n, qi,
-                              ms.w, ms.wp, s));
+  for (uint64_t i0 = 0; i0 < decomp; i0 += kParamBlock) {
+    const uint64_t cnt = std::min<uint64_t>(kParamBlock, decomp - i0);
+    KsModuli round_mods, fin_mods;
+    for (uint64_t e = 0; e < cnt; ++e) {
+      const uint64_t qi = moduli[i0 + e], mu_i = nt::multiply_factor(1, 64, qi);
+      round_mods.m[e] = KsModulus{qi, mu_i, qi - ((q_last >> 1) % qi), 0, 0};
+      const Twiddle ms = make_twiddle(modswitch[i0 + e] % qi, qi);
+      fin_mods.m[e] = KsModulus{qi, mu_i, ms.w, ms.wp, 0};
+    }
+    uint64_t* tmp_c = tmp + i0 * kcc * n;
+    LAUNCH(launch_ks_round(tmp_c, t_last, n, kcc, q_last, mu_last, cnt, round_mods, s));
+    if (int rc = ntt_multi_on_device(true, dev, h.data() + i0, cnt, tmp_c, tmp_c, 4, kcc, s)) return rc;
+    LAUNCH(launch_ks_finish(result, prod + i0 * kcc * n, tmp_c, n, kcc, decomp, i0, cnt, fin_mods, s));
   }
 #undef LAUNCH
   return 0;  // asynchronous on s; ~Scratch returns the buffers to the pool in stream order
+}
+
+constexpr u64 kFastLo = 1ull << 32, kFastHi = 1ull << 56;  // moduli eligible for the FAST butterflies (ntt_kernels.cuh)
+
+// `count` handles x `group` polynomials each, device pointers on device `dev`, in blocks of kParamBlock handles
+int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
+                        const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s) {
+  const uint64_t n = handles[0]->n;
+  for (uint64_t first = 0; first < count; first += kParamBlock) {
+    const uint64_t cnt = std::min<uint64_t>(kParamBlock, count - first);
+    NttMulti multi{};
+    multi.group = (unsigned)group;
+    bool all_fast = true;
+    for (uint64_t i = 0; i < cnt; ++i) {
+      NttDeviceTables t;
+      if (int rc = device_tables(handles[first + i], dev, &t)) return rc;
+      multi.p[i] = t.dparams;
+      all_fast = all_fast && t.q >= kFastLo && t.q < kFastHi;
+    }
+    const uint64_t off = first * group * n;
+    cudaError_t e = launch_ntt_multi(forward, multi, handles[0]->log_n, all_fast, result + off, operand + off, out_mf,
+                                     cnt * group, s);
+    if (e != cudaSuccess) return cuda_fail(e, "multi-modulus NTT launch");
+  }
+  return 0;
+}
+
+int ntt_compute_multi(bool forward, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
+                      const uint64_t* operand, uint64_t in_mf, uint64_t out_mf, uint64_t group, void* stream) {
+  if (!handles) return fail(HEXL_B200_ERR_INVALID_ARG, "handles == nullptr");
+  if (count == 0 || group == 0) return 0;
+  for (uint64_t i = 0; i < count; ++i) {
+    if (!handles[i]) return fail(HEXL_B200_ERR_INVALID_ARG, "handles[%llu] == nullptr", (unsigned long long)i);
+    if (handles[i]->n != handles[0]->n) return fail(HEXL_B200_ERR_INVALID_ARG, "all handles must share one degree");
+  }
+  if (count == 1) return ntt_compute(forward, handles[0], result, operand, in_mf, out_mf, group, stream);
+  if (!result) return fail(HEXL_B200_ERR_INVALID_ARG, "result == nullptr");
+  if (!operand) return fail(HEXL_B200_ERR_INVALID_ARG, "operand == nullptr");
+  const bool in_ok = forward ? (in_mf == 1 || in_mf == 2 || in_mf == 4) : (in_mf == 1 || in_mf == 2);
+  const bool out_ok = forward ? (out_mf == 1 || out_mf == 4) : (out_mf == 1 || out_mf == 2);
+  if (!in_ok || !out_ok) return fail(HEXL_B200_ERR_INVALID_ARG, "bad input/output_mod_factor");
+  PtrInfo pi;
+  if (int rc = classify_all({result, operand}, &pi)) return rc;
+  const uint64_t n = handles[0]->n;
+  if (pi.where == Where::Host) {  // staged path, one modulus at a time
+    for (uint64_t i = 0; i < count; ++i)
+      if (int rc = ntt_compute(forward, handles[i], result + i * group * n, operand + i * group * n, in_mf, out_mf,
+                               group, stream))
+        return rc;
+    return 0;
+  }
+  for (uint64_t i = 0; i < count; ++i)
+    if (int rc = check_bounds(operand + i * group * n, group * n, handles[i]->q * in_mf, pi, "operand")) return rc;
+  DeviceGuard g;
+  if (int rc = g.enter(pi.device)) return rc;
+  if (int rc = ntt_multi_on_device(forward, pi.device, handles, count, result, operand, (int)out_mf, group,
+                                   (cudaStream_t)stream))
+    return rc;
+  return finish_device_call(pi, stream);
 }
 
 int debug_bounds(const u64* p, u64 n, u64 bound, const char* what, std::initializer_list<const void*> all) {
@@ -784,6 +853,7 @@ void hexl_b200_ntt_release(hexl_b200_ntt* h) {
       cudaFree(kv.second.inv);
       cudaFree(kv.second.fwd32);  // nullptr unless q < 2^30
       cudaFree(kv.second.inv32);
+      cudaFree(kv.second.params);
     }
   }
   if (prev >= 0) cudaSetDevice(prev);
@@ -815,6 +885,17 @@ int hexl_b200_ntt_forward(hexl_b200_ntt* h, uint64_t* result, const uint64_t* op
 int hexl_b200_ntt_inverse(hexl_b200_ntt* h, uint64_t* result, const uint64_t* operand, uint64_t in_mf,
                           uint64_t out_mf, uint64_t batch, void* stream) {
   return ntt_compute(false, h, result, operand, in_mf, out_mf, batch, stream);
+}
+
+int hexl_b200_ntt_forward_multi(hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
+                                const uint64_t* operand, uint64_t in_mf, uint64_t out_mf, uint64_t batch_per_modulus,
+                                void* stream) {
+  return ntt_compute_multi(true, handles, count, result, operand, in_mf, out_mf, batch_per_modulus, stream);
+}
+int hexl_b200_ntt_inverse_multi(hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
+                                const uint64_t* operand, uint64_t in_mf, uint64_t out_mf, uint64_t batch_per_modulus,
+                                void* stream) {
+  return ntt_compute_multi(false, handles, count, result, operand, in_mf, out_mf, batch_per_modulus, stream);
 }
 
 // ---- eltwise.  Checks mirror the HEXL_CHECKs at the top of each reference op.

@@ -37,6 +37,16 @@ cudaError_t launch_eltwise(EltOp op, const EltParams& p, cudaStream_t stream);
 //           ntt-internal.cpp:144-154; here they keep the tree indexing)
 // The children of node k are 2k and 2k+1; a sub-transform rooted at node b uses
 // node b*2^s + i for its stage s, group i.
+//
+// NttDeviceParams: what a kernel needs to know about one (N, q), resident in device
+// memory next to the tables, so that ONE launch can transform polynomials of several
+// moduli (RNS batches): the launch carries a short list of pointers to these records.
+struct NttDeviceParams {
+  const Twiddle* fwd;
+  const Twiddle* inv;
+  u64 q, mu;
+  Twiddle inv_n, inv_n_w;
+};
 struct NttDeviceTables {
   const Twiddle* fwd;
   const Twiddle* inv;
@@ -49,6 +59,7 @@ struct NttDeviceTables {
   Twiddle inv_n;    // N^-1 and its Shoup factor
   Twiddle inv_n_w;  // N^-1 * inv[1] and its Shoup factor
   Twiddle32 inv_n32, inv_n_w32;
+  const NttDeviceParams* dparams;  // the same facts as a device-resident record
 };
 constexpr u64 kSmallModulusLimit = 1ull << 30;  // below: 4q < 2^32, the 32-bit kernels apply
 
@@ -58,14 +69,23 @@ cudaError_t launch_ntt_forward(const NttDeviceTables& t, u64* result, const u64*
 cudaError_t launch_ntt_inverse(const NttDeviceTables& t, u64* result, const u64* operand,
                                int in_mf, int out_mf, u64 batch, cudaStream_t stream);
 
+// Multi-modulus launch: polynomial u (of `units` back to back) belongs to entry u / group.
+// At most kParamBlock entries per call; all moduli share the degree 2^log_n.
+constexpr int kParamBlock = 64;
+struct NttMulti {
+  const NttDeviceParams* p[kParamBlock];
+  unsigned group;
+};
+cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, bool all_fast, u64* result,
+                             const u64* operand, int out_mf, u64 units, cudaStream_t stream);
+
 // ----------------------------------------------------- SEAL-shaped composites
 struct DyadicModulus {  // per RNS modulus: q and its generalised-Barrett constants
   u64 q, mu;
   int shift;
 };
 // Small per-call tables travel as kernel parameters (no upload, no synchronisation, capturable
-// in a CUDA graph); longer lists are processed in blocks of this many entries.
-constexpr int kParamBlock = 64;
+// in a CUDA graph); longer lists are processed in blocks of kParamBlock entries.
 struct DyadicModuli {
   DyadicModulus m[kParamBlock];
 };
@@ -75,14 +95,29 @@ struct KeyPointers {
 // moduli [first, first + count) of a DyadicMultiply over `num_moduli` moduli
 cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli, u64 first,
                                    u64 count, const DyadicModuli& mods, cudaStream_t stream);
-// digits [0, count) of `keys`/`operands`; accumulate != 0 adds to the value already in prod_i (mod q)
-cudaError_t launch_ks_mac(u64* prod_i, const u64* operands, const KeyPointers& keys, u64 n, u64 count, u64 kcc,
-                          u64 key_index, u64 key_modulus_size, u64 prod_stride_k, u64 q, u64 mu, Twiddle r64,
-                          int accumulate, cudaStream_t stream);
-cudaError_t launch_ks_round(u64* out, const u64* t_last, u64 n, u64 q_last, u64 mu_last, u64 q_i, u64 mu_i, u64 fix,
-                            cudaStream_t stream);
-cudaError_t launch_ks_finish(u64* result, const u64* prod, const u64* t_ntt, u64 n, u64 q, u64 ms, u64 ms_p,
+// KeySwitch glue, batched over the RNS moduli of one parameter block (entry e of `mods`
+// describes modulus i0 + e).  KsModulus.a/b/c mean, per kernel:
+//   reduce: -            mac: a,b = 2^64 mod q and its Shoup factor, c = slot of q in the key
+//   round:  a = q - (q_last/2 mod q)        finish: a,b = mod-switch factor and its Shoup factor
+struct KsModulus {
+  u64 q, mu, a, b, c;
+};
+struct KsModuli {
+  KsModulus m[kParamBlock];
+};
+// ops[e][j][l] = t_coef[j][l] mod q_e                     (e < count, j < decomp, l < n)
+cudaError_t launch_ks_reduce(u64* ops, const u64* t_coef, u64 n, u64 decomp, u64 count, const KsModuli& mods,
                              cudaStream_t stream);
+// prod[e][k][l] (+)= sum_{j < jcount} ops[e][j][l] * keys[j][k][c_e][l]  mod q_e ; ops_stride = elements between e's
+cudaError_t launch_ks_mac(u64* prod, const u64* ops, u64 ops_stride, const KeyPointers& keys, u64 n, u64 jcount,
+                          u64 kcc, u64 key_modulus_size, u64 count, const KsModuli& mods, int accumulate,
+                          cudaStream_t stream);
+// tmp[e][k][l] = ((t_last[k][l] + q_last/2) mod q_last) mod q_e + a_e
+cudaError_t launch_ks_round(u64* tmp, const u64* t_last, u64 n, u64 kcc, u64 q_last, u64 mu_last, u64 count,
+                            const KsModuli& mods, cudaStream_t stream);
+// result[k][i0+e][l] = (result + (prod[e][k][l] + 4 q_e - tmp[e][k][l]) * a_e) mod q_e ; result has `decomp` moduli per k
+cudaError_t launch_ks_finish(u64* result, const u64* prod, const u64* tmp, u64 n, u64 kcc, u64 decomp, u64 i0,
+                             u64 count, const KsModuli& mods, cudaStream_t stream);
 
 // launches issued so far (all kernels of this library)
 void count_launch(unsigned n = 1);

@@ -1,0 +1,215 @@
+// Multi-modulus NTT launches: ONE launch transforms `units` polynomials back to back,
+// polynomial u under the modulus of entry u / group.  This is the RNS shape of the
+// callers of the reference's NTT (every ciphertext polynomial exists once per modulus;
+// KeySwitch re-transforms every digit under every modulus, key-switch-internal.cpp:60-131):
+// with one launch per (polynomial, modulus) those workloads are bound by launch latency,
+// not by arithmetic.  Same kernels bodies as ntt.cu; the only difference is where the
+// twiddle pointer and the modulus constants come from -- a device-resident record per
+// (N, q) (NttDeviceParams) found through a pointer list in the kernel parameters.
+#include "ntt_kernels.cuh"
+
+namespace hexl_b200 {
+namespace {
+
+__device__ __forceinline__ NttDeviceParams load_params(const NttMulti& multi, u64 poly) {
+  return *multi.p[poly / multi.group];  // uniform across the CTA (a CTA never spans two polynomials' moduli)
+}
+
+// rows of one CTA must share a modulus: ROWS divides rows_per_poly * group or the launcher
+// falls back to one row per ... (see launch_row_multi: grid is built per polynomial row set)
+template <int MODE, int LOGC, bool FWD>
+__global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE>::MIN_BLOCKS)
+    ntt_row_multi(u64* result, const u64* operand, const __grid_constant__ NttMulti multi, u64 total_rows,
+                  unsigned rows_per_poly, int out_mf, int fold) {
+  using Cfg = RowCfg<LOGC, MODE>;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const unsigned row_local = threadIdx.x / Cfg::T, u = threadIdx.x % Cfg::T;
+  u64 row = (u64)blockIdx.x * Cfg::ROWS + row_local;
+  const bool active = row < total_rows;
+  if (!active) row = total_rows - 1;
+  const NttDeviceParams P = load_params(multi, row / rows_per_poly);
+  const Mod m = make_mod(P.q, P.mu);
+  const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
+  typename Cfg::E* srow = reinterpret_cast<typename Cfg::E*>(smem + (size_t)row_local * Cfg::ROW_BYTES);
+  if (FWD)
+    row_fwd_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C, srow, u, base, P.fwd, m,
+                                               out_mf, active);
+  else
+    row_inv_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C, srow, u, base, P.inv, m,
+                                               out_mf, fold != 0, P.inv_n, P.inv_n_w, active);
+}
+
+template <int MODE, int LOGR, bool FWD>
+__global__ void __launch_bounds__(256)
+    ntt_col_multi(u64* result, const u64* operand, const __grid_constant__ NttMulti multi, int log_n, int log_s,
+                  u64 total_cols, int out_mf, int fold) {
+  constexpr int R = 1 << LOGR;
+  __shared__ Twiddle stw[R];
+  const int log_cols = log_s - LOGR;
+  const u64 g0 = (u64)blockIdx.x * blockDim.x;
+  const u64 blk = g0 >> log_cols;                    // sub-block index over the whole batch
+  const u64 blocks_per_poly = 1ull << (log_n - log_s);
+  const NttDeviceParams P = load_params(multi, blk >> (log_n - log_s));
+  const Mod m = make_mod(P.q, P.mu);
+  const Twiddle* tw = FWD ? P.fwd : P.inv;
+  const u64 base = blocks_per_poly + (blk & (blocks_per_poly - 1));
+  for (int l = threadIdx.x; l < R; l += blockDim.x) {
+    if (l == 0) continue;
+    const int s = 31 - __clz(l);
+    stw[l] = ld_tw(tw + (base << s) + (l - (1 << s)));
+  }
+  __syncthreads();
+  const u64 g = g0 + threadIdx.x;
+  if (g >= total_cols) return;
+  const u64 c = g & ((1ull << log_cols) - 1);
+  col_body<MODE, LOGR, FWD, kStream, kStream>(result, operand, (blk << log_s) + c, log_cols, stw, m, out_mf,
+                                              !FWD && fold && log_s == log_n, P.inv_n, P.inv_n_w);
+}
+
+// N < 16: one thread per polynomial, everything in registers (launch-bound shapes only)
+template <bool FWD>
+__global__ void ntt_tiny_multi(u64* result, const u64* operand, const __grid_constant__ NttMulti multi, int log_n,
+                               u64 units, int out_mf) {
+  const u64 unit = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (unit >= units) return;
+  const NttDeviceParams P = *multi.p[unit / multi.group];
+  const Mod m = make_mod(P.q, P.mu);
+  const int n = 1 << log_n;
+  u64 v[8];
+  for (int e = 0; e < n; ++e) v[e] = operand[unit * n + e];
+  for (int k = 0; k < log_n; ++k) {
+    const int s = FWD ? k : log_n - 1 - k;  // stage: 2^s groups, span t
+    const int t = n >> (s + 1);
+    for (int i = 0; i < (1 << s); ++i)
+      for (int j = 0; j < t; ++j) {
+        u64& X = v[2 * i * t + j];
+        u64& Y = v[2 * i * t + j + t];
+        if (FWD)
+          fwd_bfly<kGeneric>(X, Y, P.fwd[(1 << s) + i], m);
+        else if (s == 0)
+          inv_bfly_last(X, Y, P.inv_n, P.inv_n_w, m, m.two_q);
+        else
+          inv_bfly<kGeneric>(X, Y, P.inv[(1 << s) + i], m, m.two_q);
+      }
+  }
+  for (int e = 0; e < n; ++e) result[unit * n + e] = FWD ? fwd_out<kGeneric>(v[e], m, out_mf) : inv_out(v[e], m, out_mf);
+}
+
+template <int MODE, int LOGC>
+cudaError_t launch_row_multi(bool fwd, const NttMulti& multi, int log_n, u64* result, const u64* operand, u64 units,
+                             int out_mf, int fold, cudaStream_t stream) {
+  using Cfg = RowCfg<LOGC, MODE>;
+  const unsigned rows_per_poly = 1u << (log_n - LOGC);
+  const u64 total_rows = units * rows_per_poly;
+  const unsigned grid = (unsigned)((total_rows + Cfg::ROWS - 1) / Cfg::ROWS);
+  if (fwd) {
+    if (Cfg::SMEM > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(ntt_row_multi<MODE, LOGC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)Cfg::SMEM);
+      if (e != cudaSuccess) return e;
+    }
+    ntt_row_multi<MODE, LOGC, true><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, total_rows,
+                                                                               rows_per_poly, out_mf, fold);
+  } else {
+    if (Cfg::SMEM > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(ntt_row_multi<MODE, LOGC, false>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+      if (e != cudaSuccess) return e;
+    }
+    ntt_row_multi<MODE, LOGC, false><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, total_rows,
+                                                                                rows_per_poly, out_mf, fold);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_row_multi_dyn(int log_c, bool fwd, const NttMulti& multi, int log_n, u64* result,
+                                 const u64* operand, u64 units, int out_mf, int fold, cudaStream_t stream) {
+  switch (log_c) {
+#define ROW_CASE(L) \
+  case L: return launch_row_multi<MODE, L>(fwd, multi, log_n, result, operand, units, out_mf, fold, stream);
+    ROW_CASE(4) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7) ROW_CASE(8) ROW_CASE(9) ROW_CASE(10)
+    ROW_CASE(11) ROW_CASE(12) ROW_CASE(13) ROW_CASE(14)
+#undef ROW_CASE
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <int MODE, int LOGR>
+cudaError_t launch_col_multi(bool fwd, const NttMulti& multi, int log_n, u64* result, const u64* operand, u64 units,
+                             int log_s, int out_mf, int fold, cudaStream_t stream) {
+  const u64 total_cols = (units << log_n) >> LOGR;
+  const u64 cols_per_block = 1ull << (log_s - LOGR);
+  const unsigned threads = (unsigned)(cols_per_block < 256 ? cols_per_block : 256);
+  const unsigned grid = (unsigned)((total_cols + threads - 1) / threads);
+  if (fwd)
+    ntt_col_multi<MODE, LOGR, true><<<grid, threads, 0, stream>>>(result, operand, multi, log_n, log_s, total_cols,
+                                                                  out_mf, fold);
+  else
+    ntt_col_multi<MODE, LOGR, false><<<grid, threads, 0, stream>>>(result, operand, multi, log_n, log_s, total_cols,
+                                                                   out_mf, fold);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_col_multi_dyn(int log_r, bool fwd, const NttMulti& multi, int log_n, u64* result,
+                                 const u64* operand, u64 units, int log_s, int out_mf, int fold, cudaStream_t stream) {
+  switch (log_r) {
+#define COL_CASE(L) \
+  case L: return launch_col_multi<MODE, L>(fwd, multi, log_n, result, operand, units, log_s, out_mf, fold, stream);
+    COL_CASE(1) COL_CASE(2) COL_CASE(3) COL_CASE(4) COL_CASE(5)
+#undef COL_CASE
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <int MODE>
+cudaError_t multi_impl(bool fwd, const NttMulti& multi, int log_n, u64* result, const u64* operand, int out_mf,
+                       u64 units, cudaStream_t stream) {
+  const int log_c = pick_row_log(log_n);
+  int radices[8];
+  const int ncol = plan_col_passes(log_n - log_c, radices);
+  if (fwd) {
+    const u64* src = operand;
+    int log_s = log_n;
+    for (int p = 0; p < ncol; ++p) {
+      cudaError_t e = launch_col_multi_dyn<MODE>(radices[p], true, multi, log_n, result, src, units, log_s, out_mf, 0, stream);
+      if (e != cudaSuccess) return e;
+      log_s -= radices[p];
+      src = result;
+    }
+    return launch_row_multi_dyn<MODE>(log_c, true, multi, log_n, result, src, units, out_mf, 0, stream);
+  }
+  cudaError_t e = launch_row_multi_dyn<MODE>(log_c, false, multi, log_n, result, operand, units, out_mf, ncol == 0, stream);
+  if (e != cudaSuccess) return e;
+  int log_s = log_c;
+  for (int p = ncol - 1; p >= 0; --p) {
+    log_s += radices[p];
+    e = launch_col_multi_dyn<MODE>(radices[p], false, multi, log_n, result, result, units, log_s, out_mf, p == 0, stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace
+
+cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, bool all_fast, u64* result,
+                             const u64* operand, int out_mf, u64 units, cudaStream_t stream) {
+  if (units == 0) return cudaSuccess;
+  if (log_n < 4) {
+    const unsigned threads = 128, grid = (unsigned)((units + threads - 1) / threads);
+    if (forward)
+      ntt_tiny_multi<true><<<grid, threads, 0, stream>>>(result, operand, multi, log_n, units, out_mf);
+    else
+      ntt_tiny_multi<false><<<grid, threads, 0, stream>>>(result, operand, multi, log_n, units, out_mf);
+    count_launch();
+    return cudaGetLastError();
+  }
+  static const bool force_generic = env_int("HEXL_B200_FORCE_GENERIC", 0) != 0;
+  return (all_fast && !force_generic) ? multi_impl<kFast>(forward, multi, log_n, result, operand, out_mf, units, stream)
+                                      : multi_impl<kGeneric>(forward, multi, log_n, result, operand, out_mf, units, stream);
+}
+
+}  // namespace hexl_b200

@@ -47,60 +47,81 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
-// ---- KeySwitch: lazy 128-bit multiply-accumulate with the switching keys and
-// the final reduction (key-switch-internal.cpp:93-130).  For RNS modulus i
-// (key_index = its slot in the key), thread (k, l) sums over the decomposition
-// digits j:  acc += operand[j][l] * key_j[n*key_index + k*key_modulus_size*n + l]
-// and stores acc mod q.  acc = hi*2^64 + lo is reduced as
-// Shoup(hi, 2^64 mod q) + Barrett(lo), both lazy, then two conditional subtractions.
+// ---- KeySwitch glue (key-switch-internal.cpp:60-198), every kernel batched over the RNS
+// moduli of one parameter block; layouts are [modulus][component or digit][n].
+
+// :77-85: every digit, in coefficient form, reduced into modulus e.  The reference copies
+// when q_j <= q_e (the value is already < q_e) and reduces otherwise; one Barrett does both.
 __global__ void __launch_bounds__(kThreads)
-    ks_mac_kernel(u64* prod_i /* [kcc][rns*n] slice base + i*n */, const u64* operands /* [count][n] */,
-                  const __grid_constant__ KeyPointers keys, u64 n, u64 count, u64 kcc, u64 key_index,
-                  u64 key_modulus_size, u64 prod_stride_k, u64 q, u64 mu, Twiddle r64, int accumulate) {
-  const u64 total = kcc * n;
+    ks_reduce_kernel(u64* ops, const u64* t_coef, u64 per_mod /* decomp*n */, u64 count,
+                     const __grid_constant__ KsModuli mods) {
+  const u64 total = per_mod * count;
+  const u64 stride = (u64)gridDim.x * kThreads;
+  for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < total; g += stride) {
+    const u64 e = g / per_mod, src = g - e * per_mod;
+    const KsModulus& md = mods.m[e];
+    ops[g] = csub(barrett64_lazy(t_coef[src], md.q, md.mu), md.q);
+  }
+}
+
+// :93-130: lazy 128-bit multiply-accumulate of the digits with the switching keys, one
+// Shoup(hi, 2^64 mod q) + Barrett(lo) at the end, two conditional subtractions.
+__global__ void __launch_bounds__(kThreads)
+    ks_mac_kernel(u64* prod, const u64* ops, u64 ops_stride, const __grid_constant__ KeyPointers keys, u64 n,
+                  u64 jcount, u64 kcc, u64 key_modulus_size, u64 count, const __grid_constant__ KsModuli mods,
+                  int accumulate) {
+  const u64 per_mod = kcc * n;
   const u64 g = (u64)blockIdx.x * kThreads + threadIdx.x;
-  if (g >= total) return;
-  const u64 k = g / n, l = g - k * n;
-  const u64 key_off = n * key_index + k * key_modulus_size * n + l;
+  if (g >= per_mod * count) return;
+  const u64 e = g / per_mod, r = g - e * per_mod;
+  const u64 k = r / n, l = r - k * n;
+  const KsModulus& md = mods.m[e];
+  const u64 key_off = n * md.c + k * key_modulus_size * n + l;
+  const u64* op = ops + e * ops_stride + l;
   u64 lo = 0, hi = 0;
-  for (u64 j = 0; j < count; ++j) {
-    const u64 a = operands[j * n + l];
+  for (u64 j = 0; j < jcount; ++j) {
+    const u64 a = op[j * n];
     const u64 b = __ldcs(keys.p[j] + key_off);
     const u64 plo = a * b, phi = mulhi(a, b);
     lo += plo;
     hi += phi + (lo < plo);
   }
-  u64 r = shoup_lazy(hi, r64.w, r64.wp, q) + barrett64_lazy(lo, q, mu);  // < 4q
-  r = csub(csub(r, q << 1), q);
-  u64* dst = prod_i + k * prod_stride_k + l;
-  if (accumulate) r = csub(r + *dst, q);
-  *dst = r;
+  u64 v = shoup_lazy(hi, md.a, md.b, md.q) + barrett64_lazy(lo, md.q, md.mu);  // < 4q
+  v = csub(csub(v, md.q << 1), md.q);
+  if (accumulate) v = csub(v + prod[g], md.q);
+  prod[g] = v;
 }
 
-// ---- KeySwitch tail, first half (key-switch-internal.cpp:148-178): the special
-// prime's part, already in coefficient form in [0, 2*q_last):
-//   t = (x + q_last/2) mod q_last;   out_i = (t mod q_i) + (q_i - (q_last/2 mod q_i))
-// written for every target modulus i at out + i*kcc_stride (lazy, < 2 q_i).
+// :148-178: the special prime's part (coefficient form, [0, 2 q_last)), rounded and moved
+// into modulus e:  t = (x + q_last/2) mod q_last;  out = (t mod q_e) + (q_e - (q_last/2 mod q_e))
 __global__ void __launch_bounds__(kThreads)
-    ks_round_kernel(u64* out, const u64* t_last, u64 n, u64 q_last, u64 mu_last, u64 q_i, u64 mu_i, u64 fix) {
-  const u64 l = (u64)blockIdx.x * kThreads + threadIdx.x;
-  if (l >= n) return;
-  u64 x = t_last[l] + (q_last >> 1);
+    ks_round_kernel(u64* tmp, const u64* t_last, u64 per_mod /* kcc*n */, u64 q_last, u64 mu_last, u64 count,
+                    const __grid_constant__ KsModuli mods) {
+  const u64 g = (u64)blockIdx.x * kThreads + threadIdx.x;
+  if (g >= per_mod * count) return;
+  const u64 e = g / per_mod, r = g - e * per_mod;
+  const KsModulus& md = mods.m[e];
+  u64 x = t_last[r] + (q_last >> 1);
   x = csub(barrett64_lazy(x, q_last, mu_last), q_last);
-  if (q_last > q_i) x = csub(barrett64_lazy(x, q_i, mu_i), q_i);
-  out[l] = x + fix;
+  if (q_last > md.q) x = csub(barrett64_lazy(x, md.q, md.mu), md.q);
+  tmp[g] = x + md.a;
 }
 
-// ---- KeySwitch tail, second half (:183-197):
-//   ith = prod + 4 q_i - t_ntt;  r = ith * modswitch mod q_i (inputs < 8 q_i);  result = (result + r) mod q_i
+// :183-197:  r = (prod + 4 q_e - t_ntt) * modswitch mod q_e (operand < 8 q_e);  result += r mod q_e
 __global__ void __launch_bounds__(kThreads)
-    ks_finish_kernel(u64* result, const u64* prod, const u64* t_ntt, u64 n, u64 q, u64 ms, u64 ms_p) {
-  const u64 l = (u64)blockIdx.x * kThreads + threadIdx.x;
-  if (l >= n) return;
-  u64 x = prod[l] + (q << 2) - t_ntt[l];
-  x = reduce_from<8>(x, q);
-  const u64 r = csub(shoup_lazy(x, ms, ms_p, q), q);
-  result[l] = csub(result[l] + r, q);
+    ks_finish_kernel(u64* result, const u64* prod, const u64* tmp, u64 n, u64 kcc, u64 decomp, u64 i0, u64 count,
+                     const __grid_constant__ KsModuli mods) {
+  const u64 per_mod = kcc * n;
+  const u64 g = (u64)blockIdx.x * kThreads + threadIdx.x;
+  if (g >= per_mod * count) return;
+  const u64 e = g / per_mod, r = g - e * per_mod;
+  const u64 k = r / n, l = r - k * n;
+  const KsModulus& md = mods.m[e];
+  u64 x = prod[g] + (md.q << 2) - tmp[g];
+  x = reduce_from<8>(x, md.q);
+  const u64 v = csub(shoup_lazy(x, md.a, md.b, md.q), md.q);
+  u64* dst = result + n * (decomp * k + i0 + e) + l;
+  *dst = csub(*dst + v, md.q);
 }
 
 unsigned blocks_for(u64 items) { return (unsigned)((items + kThreads - 1) / kThreads); }
@@ -121,25 +142,39 @@ cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_ks_mac(u64* prod_i, const u64* operands, const KeyPointers& keys, u64 n, u64 count, u64 kcc,
-                          u64 key_index, u64 key_modulus_size, u64 prod_stride_k, u64 q, u64 mu, Twiddle r64,
-                          int accumulate, cudaStream_t stream) {
-  ks_mac_kernel<<<blocks_for(kcc * n), kThreads, 0, stream>>>(prod_i, operands, keys, n, count, kcc, key_index,
-                                                             key_modulus_size, prod_stride_k, q, mu, r64, accumulate);
-  count_launch();
-  return cudaGetLastError();
-}
-
-cudaError_t launch_ks_round(u64* out, const u64* t_last, u64 n, u64 q_last, u64 mu_last, u64 q_i, u64 mu_i, u64 fix,
-                            cudaStream_t stream) {
-  ks_round_kernel<<<blocks_for(n), kThreads, 0, stream>>>(out, t_last, n, q_last, mu_last, q_i, mu_i, fix);
-  count_launch();
-  return cudaGetLastError();
-}
-
-cudaError_t launch_ks_finish(u64* result, const u64* prod, const u64* t_ntt, u64 n, u64 q, u64 ms, u64 ms_p,
+cudaError_t launch_ks_reduce(u64* ops, const u64* t_coef, u64 n, u64 decomp, u64 count, const KsModuli& mods,
                              cudaStream_t stream) {
-  ks_finish_kernel<<<blocks_for(n), kThreads, 0, stream>>>(result, prod, t_ntt, n, q, ms, ms_p);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  u64 blocks = blocks_for(decomp * n * count);
+  if (blocks > (u64)sms * 16) blocks = (u64)sms * 16;
+  ks_reduce_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(ops, t_coef, decomp * n, count, mods);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ks_mac(u64* prod, const u64* ops, u64 ops_stride, const KeyPointers& keys, u64 n, u64 jcount,
+                          u64 kcc, u64 key_modulus_size, u64 count, const KsModuli& mods, int accumulate,
+                          cudaStream_t stream) {
+  ks_mac_kernel<<<blocks_for(kcc * n * count), kThreads, 0, stream>>>(prod, ops, ops_stride, keys, n, jcount, kcc,
+                                                                     key_modulus_size, count, mods, accumulate);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ks_round(u64* tmp, const u64* t_last, u64 n, u64 kcc, u64 q_last, u64 mu_last, u64 count,
+                            const KsModuli& mods, cudaStream_t stream) {
+  ks_round_kernel<<<blocks_for(kcc * n * count), kThreads, 0, stream>>>(tmp, t_last, kcc * n, q_last, mu_last, count,
+                                                                       mods);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ks_finish(u64* result, const u64* prod, const u64* tmp, u64 n, u64 kcc, u64 decomp, u64 i0,
+                             u64 count, const KsModuli& mods, cudaStream_t stream) {
+  ks_finish_kernel<<<blocks_for(kcc * n * count), kThreads, 0, stream>>>(result, prod, tmp, n, kcc, decomp, i0, count,
+                                                                        mods);
   count_launch();
   return cudaGetLastError();
 }

@@ -348,6 +348,26 @@ class NTT {
         hexl_b200_ntt_inverse(m_handle, result, operand, input_mod_factor, output_mod_factor, batch, stream));
   }
 
+  // RNS batches in one launch (not in the reference, which needs one call per polynomial and
+  // modulus): of the count * batch_per_modulus polynomials laid out back to back, polynomial u
+  // is transformed under ntts[u / batch_per_modulus].
+  static void ComputeForwardMulti(const NTT* const* ntts, size_t count, uint64_t* result, const uint64_t* operand,
+                                  uint64_t input_mod_factor, uint64_t output_mod_factor,
+                                  uint64_t batch_per_modulus = 1, void* stream = nullptr) {
+    std::vector<hexl_b200_ntt*> hs(count);
+    for (size_t i = 0; i < count; ++i) hs[i] = ntts[i]->m_handle;
+    b200_detail::Throw(hexl_b200_ntt_forward_multi(hs.data(), count, result, operand, input_mod_factor,
+                                                   output_mod_factor, batch_per_modulus, stream));
+  }
+  static void ComputeInverseMulti(const NTT* const* ntts, size_t count, uint64_t* result, const uint64_t* operand,
+                                  uint64_t input_mod_factor, uint64_t output_mod_factor,
+                                  uint64_t batch_per_modulus = 1, void* stream = nullptr) {
+    std::vector<hexl_b200_ntt*> hs(count);
+    for (size_t i = 0; i < count; ++i) hs[i] = ntts[i]->m_handle;
+    b200_detail::Throw(hexl_b200_ntt_inverse_multi(hs.data(), count, result, operand, input_mod_factor,
+                                                   output_mod_factor, batch_per_modulus, stream));
+  }
+
   uint64_t GetMinimalRootOfUnity() const { return hexl_b200_ntt_minimal_root(m_handle); }
   uint64_t GetDegree() const { return hexl_b200_ntt_degree(m_handle); }
   uint64_t GetModulus() const { return hexl_b200_ntt_modulus(m_handle); }

@@ -123,6 +123,20 @@ int hexl_b200_ntt_inverse(hexl_b200_ntt* h, uint64_t* result, const uint64_t* op
                           uint64_t input_mod_factor, uint64_t output_mod_factor,
                           uint64_t batch, void* stream);
 
+/* RNS batches in ONE launch (the shape of the reference's callers: every ciphertext
+ * polynomial exists once per modulus, key-switch-internal.cpp:49-55,82-88): `count`
+ * handles of the same degree; of the count * batch_per_modulus polynomials laid out back
+ * to back, polynomial u is transformed under handles[u / batch_per_modulus], with the
+ * semantics of hexl_b200_ntt_forward / _inverse.  Device (or unified) pointers run as one
+ * launch per kernel stage regardless of `count`; host pointers fall back to one staged
+ * call per handle. */
+int hexl_b200_ntt_forward_multi(hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
+                                const uint64_t* operand, uint64_t input_mod_factor,
+                                uint64_t output_mod_factor, uint64_t batch_per_modulus, void* stream);
+int hexl_b200_ntt_inverse_multi(hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
+                                const uint64_t* operand, uint64_t input_mod_factor,
+                                uint64_t output_mod_factor, uint64_t batch_per_modulus, void* stream);
+
 /* ---- element-wise operations (hexl/include/hexl/eltwise/ *.hpp) -------------------
  * n = number of elements (for batched use pass n = batch * N: the ops are
  * position-independent). */

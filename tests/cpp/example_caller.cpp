@@ -141,6 +141,20 @@ int main(int argc, char** argv) {
           }
       }
     }
+    {
+      // RNS batch in one call: two moduli, two polynomials each, round trip
+      NTT a(32, 769), b(32, 193);
+      const NTT* list[2] = {&a, &b};
+      std::vector<uint64_t> v(4 * 32), orig;
+      for (size_t i = 0; i < v.size(); ++i) v[i] = (i * 37 + 5) % (i < 64 ? 769 : 193);
+      orig = v;
+      NTT::ComputeForwardMulti(list, 2, v.data(), v.data(), 1, 1, 2);
+      std::vector<uint64_t> first(32);
+      a.ComputeForward(first.data(), orig.data(), 1, 1);
+      if (!std::equal(first.begin(), first.end(), v.begin())) ++failures;
+      NTT::ComputeInverseMulti(list, 2, v.data(), v.data(), 1, 1, 2);
+      Expect(v, orig, "multi-modulus round trip");
+    }
     bool threw = false;
     try {
       std::vector<uint64_t> a{1, 2};
