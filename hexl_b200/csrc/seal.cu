@@ -24,26 +24,58 @@ __device__ __forceinline__ u64 mulmod(u64 x, u64 y, const MulCtx& c) {
 }
 
 // ---- DyadicMultiply: (x0*y0, x0*y1 + x1*y0, x1*y1) for every RNS modulus.
-// One thread per coefficient slot: 4 loads (32 B), 3 stores (24 B), all
-// coalesced; inputs are read before any output is written, so result may alias
-// either operand (test-dyadic-multiply.cpp:38-112).
+// A thread owns VEC consecutive coefficient slots of one modulus: 4 loads and 3 stores of
+// VEC*8 bytes, all coalesced and streaming (56 B of traffic per slot); inputs are read
+// before any output is written, so result may alias either operand
+// (test-dyadic-multiply.cpp:38-112).  VEC = 2 (128-bit accesses) when n is even and every
+// pointer is 16-byte aligned, else 1.
+template <int VEC>
+struct Slots {
+  u64 v[VEC];
+};
+template <int VEC>
+__device__ __forceinline__ Slots<VEC> ld_slots(const u64* p) {
+  Slots<VEC> r;
+  if constexpr (VEC == 2) {
+    const ulonglong2 t = ld_stream2(p);
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+  } else {
+    r.v[0] = __ldcs(p);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void st_slots(u64* p, const Slots<VEC>& r) {
+  if constexpr (VEC == 2) {
+    st_stream2(p, make_ulonglong2(r.v[0], r.v[1]));
+  } else {
+    __stcs(p, r.v[0]);
+  }
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(kThreads)
     dyadic_kernel(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli, u64 first, u64 count,
                   const __grid_constant__ DyadicModuli mods) {
-  const u64 total = n * count, poly = n * num_moduli, base = first * n;
+  const u64 total = n * count / VEC, poly = n * num_moduli, base = first * n;
   const u64 stride = (u64)gridDim.x * kThreads;
   for (u64 i = (u64)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
-    const DyadicModulus& dm = mods.m[i / n];
+    const DyadicModulus& dm = mods.m[i * VEC / n];
     const MulCtx c{dm.q, dm.mu, dm.shift};
-    const u64 o = base + i;
-    const u64 x0 = __ldcs(op1 + o), x1 = __ldcs(op1 + o + poly);
-    const u64 y0 = __ldcs(op2 + o), y1 = __ldcs(op2 + o + poly);
-    const u64 r0 = mulmod(x0, y0, c);
-    const u64 r1 = csub(mulmod(x0, y1, c) + mulmod(x1, y0, c), c.q);
-    const u64 r2 = mulmod(x1, y1, c);
-    __stcs(result + o, r0);
-    __stcs(result + o + poly, r1);
-    __stcs(result + o + 2 * poly, r2);
+    const u64 o = base + i * VEC;
+    const Slots<VEC> x0 = ld_slots<VEC>(op1 + o), x1 = ld_slots<VEC>(op1 + o + poly);
+    const Slots<VEC> y0 = ld_slots<VEC>(op2 + o), y1 = ld_slots<VEC>(op2 + o + poly);
+    Slots<VEC> r0, r1, r2;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      r0.v[k] = mulmod(x0.v[k], y0.v[k], c);
+      r1.v[k] = csub(mulmod(x0.v[k], y1.v[k], c) + mulmod(x1.v[k], y0.v[k], c), c.q);
+      r2.v[k] = mulmod(x1.v[k], y1.v[k], c);
+    }
+    st_slots<VEC>(result + o, r0);
+    st_slots<VEC>(result + o + poly, r1);
+    st_slots<VEC>(result + o + 2 * poly, r2);
   }
 }
 
@@ -135,9 +167,15 @@ cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  u64 blocks = blocks_for(total);
-  if (blocks > (u64)sms * 8) blocks = (u64)sms * 8;
-  dyadic_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(result, op1, op2, n, num_moduli, first, count, mods);
+  const bool vec = n % 2 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(result) | reinterpret_cast<uintptr_t>(op1) |
+                     reinterpret_cast<uintptr_t>(op2)) & 15) == 0;
+  u64 blocks = blocks_for(vec ? total / 2 : total);
+  if (blocks > (u64)sms * 16) blocks = (u64)sms * 16;
+  if (vec)
+    dyadic_kernel<2><<<(unsigned)blocks, kThreads, 0, stream>>>(result, op1, op2, n, num_moduli, first, count, mods);
+  else
+    dyadic_kernel<1><<<(unsigned)blocks, kThreads, 0, stream>>>(result, op1, op2, n, num_moduli, first, count, mods);
   count_launch();
   return cudaGetLastError();
 }

@@ -245,6 +245,56 @@ def test_multi_modulus_more_than_one_parameter_block(hb, checker):
     assert (host(o) == exp).all()
 
 
+def test_concurrent_host_threads(hb, checker):
+    """The reference is "single-threaded and thread-safe" (README.md:264-265): many host
+    threads may call it at once.  Eight threads share one NTT object and the NTT cache and
+    mix device-pointer calls (each on its own stream), host-pointer calls (which share the
+    per-device staging buffers) and KeySwitch-style scratch use; ctypes drops the GIL for
+    the duration of every call, so the calls really overlap."""
+    import threading
+    n = 1 << 12
+    q = hb.GeneratePrimes(1, 55, True, n)[0]
+    shared = hb.NTT(n, q)
+    mods = hb.GeneratePrimes(3, 45, True, n)
+    errors = []
+
+    def worker(tid):
+        try:
+            stream = torch.cuda.Stream()
+            for it in range(6):
+                batch = 1 + (tid + it) % 4
+                x = uniform_below(100 * tid + it, n * batch, q)
+                exp = checker.ntt_forward(x, n, q)
+                if (tid + it) % 2 == 0:
+                    with torch.cuda.stream(stream):
+                        d = dev(x)
+                        o = torch.empty_like(d)
+                        shared.ComputeForward(o, d, 1, 1, stream=stream)
+                        hb.EltwiseAddMod(o, o, o, n * batch, q, stream=stream)
+                        stream.synchronize()
+                    got = host(o)
+                    exp = (exp + exp) % np.uint64(q)
+                else:
+                    got = np.zeros_like(x)
+                    shared.ComputeForward(got, x, 1, 1)
+                assert (got == exp).all(), (tid, it)
+                cached = hb.GetNTT(n, mods[(tid + it) % 3])  # cache hit or first creation, racing with the others
+                y = uniform_below(tid + 1000 * it, n, cached.GetModulus())
+                back = np.zeros_like(y)
+                cached.ComputeForward(back, y, 1, 1)
+                cached.ComputeInverse(back, back, 1, 1)
+                assert (back == y).all(), (tid, it)
+        except Exception as exc:  # noqa: BLE001 - reported by the main thread
+            errors.append((tid, repr(exc)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_ntt_user_root(hb, checker):
     n = 256
     q = hb.GeneratePrimes(1, 40, True, n)[0]
@@ -565,6 +615,21 @@ def test_key_switch_matches_oracle(hb, checker, logn, decomp, bits):
     dres = dev(result)
     hb.KeySwitch(dres, dev(t_target), n, decomp, kms, rns, kcc, mods, [dev(x) for x in keys], modswitch)
     assert (host(dres) == exp).all()
+
+
+def test_dyadic_multiply_odd_length_and_unaligned(hb, checker):
+    """the scalar instantiation: odd coefficient count, and views that start 8 bytes off a 16-byte boundary"""
+    for n, shift in ((13, 0), (64, 1)):
+        mods = hb.GeneratePrimes(3, 40, True, 1)
+        a = np.concatenate([uniform_below(3 + i, n, q) for _ in range(2) for i, q in enumerate(mods)])
+        b = np.concatenate([uniform_below(9 + i, n, q) for _ in range(2) for i, q in enumerate(mods)])
+        da = torch.zeros(a.size + 1, dtype=torch.int64, device="cuda")
+        db = torch.zeros(b.size + 1, dtype=torch.int64, device="cuda")
+        out = torch.zeros(3 * n * len(mods) + 1, dtype=torch.int64, device="cuda")
+        da[shift:shift + a.size] = dev(a)
+        db[shift:shift + b.size] = dev(b)
+        hb.DyadicMultiply(out[shift:shift + 3 * n * len(mods)], da[shift:shift + a.size], db[shift:shift + b.size], n, mods)
+        assert (host(out[shift:shift + 3 * n * len(mods)]) == checker.dyadic_multiply(a, b, n, mods)).all(), (n, shift)
 
 
 def test_dyadic_multiply_many_moduli(hb, checker):

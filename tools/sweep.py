@@ -137,6 +137,38 @@ def main():
         print(f"* CPU reference ({threads} threads): {32 / tc / 1e3:.2f} k products/s -> GPU/CPU = {units / t / (32 / tc):.0f}x")
     del A, B
 
+    # ------------------------------------------------- multi-modulus launches vs per-modulus calls
+    print("\n## RNS batch: one ciphertext-sized unit per modulus (2 polynomials x L moduli), forward NTT, N = 2^15\n")
+    print("| L moduli | one multi-modulus launch, us | L per-modulus calls, us | ratio |")
+    print("|---|---|---|---|")
+    n = 1 << 15
+    for L in (4, 16, 30, 60):
+        mods = hb.GeneratePrimes(L, 50, True, n)
+        ntts = [hb.NTT(n, q) for q in mods]
+        x = torch.cat([torch.randint(0, q, (2 * n,), dtype=torch.int64, device="cuda", generator=g) for q in mods])
+        y = torch.empty_like(x)
+        tm = gpu_time(lambda: hb.ComputeForwardMulti(ntts, y, x, 1, 1, 2), reps=20)
+
+        def per_modulus():
+            for i, t in enumerate(ntts):
+                t.ComputeForward(y[i * 2 * n:(i + 1) * 2 * n], x[i * 2 * n:(i + 1) * 2 * n], 1, 1)
+        tp = gpu_time(per_modulus, reps=20)
+        print(f"| {L} | {tm * 1e6:.1f} | {tp * 1e6:.1f} | {tp / tm:.1f}x |")
+
+    # ------------------------------------------------------------------ DyadicMultiply
+    print("\n## DyadicMultiply (ciphertext tensor product), N = 2^15, batch of 64 ciphertext pairs as one call\n")
+    print("| L moduli | GB/s (56 B per coefficient slot) | frac of HBM peak |")
+    print("|---|---|---|")
+    for L in (8, 30):
+        big_n = n * 64  # DyadicMultiply is position-independent inside a modulus: a batch is a longer polynomial
+        mods = hb.GeneratePrimes(L, 50, True, n)
+        a = torch.cat([torch.randint(0, q, (big_n,), dtype=torch.int64, device="cuda", generator=g) for _ in range(2) for q in mods])
+        b = torch.cat([torch.randint(0, q, (big_n,), dtype=torch.int64, device="cuda", generator=g) for _ in range(2) for q in mods])
+        out = torch.empty(3 * big_n * L, dtype=torch.int64, device="cuda")
+        t = gpu_time(lambda: hb.DyadicMultiply(out, a, b, big_n, mods), reps=10)
+        print(f"| {L} | {56.0 * big_n * L / t / 1e9:.0f} | {56.0 * big_n * L / t / 1e9 / PEAK:.2f} |")
+        del a, b, out
+
     # ------------------------------------------------------- KeySwitch (config 4 shape)
     print("\n## CKKS KeySwitch composite, N = 2^15 (BASELINE configs[4] shape)\n")
     print("| decomp moduli | GPU ms / key switch | CPU reference ms | GPU/CPU |")
