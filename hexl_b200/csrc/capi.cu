@@ -49,6 +49,7 @@ struct hexl_b200_ntt {
     Twiddle32* fwd32 = nullptr;  // q < 2^30 only
     Twiddle32* inv32 = nullptr;
     NttDeviceParams* params = nullptr;
+    NttDeviceTables view{};
   };
   std::map<int, Dev> dev;  // device ordinal -> uploaded tables
 };
@@ -378,21 +379,23 @@ int device_tables(hexl_b200_ntt* h, int dev, NttDeviceTables* out) {
     NttDeviceParams hp{d.fwd, d.inv, h->q, nt::multiply_factor(1, 64, h->q), h->inv_n, h->inv_n_w};
     CU(cudaMalloc(&d.params, sizeof(NttDeviceParams)));
     CU(cudaMemcpy(d.params, &hp, sizeof(NttDeviceParams), cudaMemcpyHostToDevice));
+    NttDeviceTables& t = d.view;  // everything a launch needs, computed once
+    t.dparams = d.params;
+    t.fwd = d.fwd;
+    t.inv = d.inv;
+    t.fwd32 = d.fwd32;
+    t.inv32 = d.inv32;
+    t.inv_n32 = h->q < kSmallModulusLimit ? make_twiddle32(h->inv_n.w, h->q) : Twiddle32{0, 0};
+    t.inv_n_w32 = h->q < kSmallModulusLimit ? make_twiddle32(h->inv_n_w.w, h->q) : Twiddle32{0, 0};
+    t.n = h->n;
+    t.log_n = h->log_n;
+    t.q = h->q;
+    t.mu = hp.mu;
+    t.inv_n = h->inv_n;
+    t.inv_n_w = h->inv_n_w;
     it = h->dev.emplace(dev, d).first;
   }
-  out->dparams = it->second.params;
-  out->fwd = it->second.fwd;
-  out->inv = it->second.inv;
-  out->fwd32 = it->second.fwd32;
-  out->inv32 = it->second.inv32;
-  out->inv_n32 = h->q < kSmallModulusLimit ? make_twiddle32(h->inv_n.w, h->q) : Twiddle32{0, 0};
-  out->inv_n_w32 = h->q < kSmallModulusLimit ? make_twiddle32(h->inv_n_w.w, h->q) : Twiddle32{0, 0};
-  out->n = h->n;
-  out->log_n = h->log_n;
-  out->q = h->q;
-  out->mu = nt::multiply_factor(1, 64, h->q);
-  out->inv_n = h->inv_n;
-  out->inv_n_w = h->inv_n_w;
+  *out = it->second.view;
   return 0;
 }
 

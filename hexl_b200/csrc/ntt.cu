@@ -13,19 +13,11 @@ cudaError_t launch_row(bool fwd, const NttDeviceTables& t, u64* result, const u6
   const unsigned grid = (unsigned)((total_rows + Cfg::ROWS - 1) / Cfg::ROWS);
   const Mod m = make_mod(t);
   if (fwd) {
-    if (Cfg::SMEM > 48 * 1024) {  // per-device attribute: set on every launch (cheap)
-      cudaError_t e = cudaFuncSetAttribute(ntt_row_fwd<MODE, LOGC>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-      if (e != cudaSuccess) return e;
-    }
+    if (cudaError_t e = ensure_dynamic_smem<ntt_row_fwd<MODE, LOGC>>(Cfg::SMEM)) return e;
     ntt_row_fwd<MODE, LOGC><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, Tab<MODE>::fwd(t), m,
                                                                        total_rows, rows_per_poly, out_mf);
   } else {
-    if (Cfg::SMEM > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(ntt_row_inv<MODE, LOGC>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-      if (e != cudaSuccess) return e;
-    }
+    if (cudaError_t e = ensure_dynamic_smem<ntt_row_inv<MODE, LOGC>>(Cfg::SMEM)) return e;
     ntt_row_inv<MODE, LOGC><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(
         result, operand, Tab<MODE>::inv(t), m, total_rows, rows_per_poly, out_mf, fold, Tab<MODE>::inv_n(t),
         Tab<MODE>::inv_n_w(t));

@@ -28,6 +28,7 @@
 //
 // No tensor cores: this is 64-bit integer modular arithmetic (IMAD-bound).
 #pragma once
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -797,6 +798,22 @@ __global__ void ntt_stage_simple(u64* result, const u64* src, const Twiddle* __r
 }
 
 // --------------------------------------------------------------- host side
+
+// Opt a kernel into more than 48 KiB of dynamic shared memory, once per kernel and device
+// (the attribute call costs more than a launch; doing it on every call doubled the host-side
+// cost of small transforms).
+template <auto Kernel>
+cudaError_t ensure_dynamic_smem(size_t bytes) {
+  if (bytes <= 48 * 1024) return cudaSuccess;
+  static std::atomic<unsigned long long> done{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 inline int env_int(const char* name, int dflt) {
   const char* v = std::getenv(name);

@@ -103,19 +103,11 @@ cudaError_t launch_row_multi(bool fwd, const NttMulti& multi, int log_n, u64* re
   const u64 total_rows = units * rows_per_poly;
   const unsigned grid = (unsigned)((total_rows + Cfg::ROWS - 1) / Cfg::ROWS);
   if (fwd) {
-    if (Cfg::SMEM > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(ntt_row_multi<MODE, LOGC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)Cfg::SMEM);
-      if (e != cudaSuccess) return e;
-    }
+    if (cudaError_t e = ensure_dynamic_smem<ntt_row_multi<MODE, LOGC, true>>(Cfg::SMEM)) return e;
     ntt_row_multi<MODE, LOGC, true><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, total_rows,
                                                                                rows_per_poly, out_mf, fold);
   } else {
-    if (Cfg::SMEM > 48 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(ntt_row_multi<MODE, LOGC, false>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
-      if (e != cudaSuccess) return e;
-    }
+    if (cudaError_t e = ensure_dynamic_smem<ntt_row_multi<MODE, LOGC, false>>(Cfg::SMEM)) return e;
     ntt_row_multi<MODE, LOGC, false><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, total_rows,
                                                                                 rows_per_poly, out_mf, fold);
   }
