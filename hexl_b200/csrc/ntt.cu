@@ -189,6 +189,7 @@ cudaError_t launch_ntt_forward(const NttDeviceTables& t, u64* result, const u64*
   switch (pick_mode(t.q)) {
     case kFast: return forward_impl<kFast>(t, result, operand, out_mf, batch, stream);
     case kSmall: return forward_impl<kSmall>(t, result, operand, out_mf, batch, stream);
+    case kWide: return forward_impl<kWide>(t, result, operand, out_mf, batch, stream);
   }
   return forward_impl<kGeneric>(t, result, operand, out_mf, batch, stream);
 }
@@ -200,6 +201,7 @@ cudaError_t launch_ntt_inverse(const NttDeviceTables& t, u64* result, const u64*
   switch (pick_mode(t.q)) {
     case kFast: return inverse_impl<kFast>(t, result, operand, out_mf, batch, stream);
     case kSmall: return inverse_impl<kSmall>(t, result, operand, out_mf, batch, stream);
+    case kWide: return inverse_impl<kWide>(t, result, operand, out_mf, batch, stream);
   }
   return inverse_impl<kGeneric>(t, result, operand, out_mf, batch, stream);
 }

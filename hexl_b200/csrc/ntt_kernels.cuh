@@ -61,6 +61,11 @@ namespace {
 //    Barrett-reduced at the pass boundary (4 of 16 for a 4-stage pass).  The
 //    largest transient is 2 * 8*2^4 * q = 256q < 2^64 for q < 2^56.
 //
+//  WIDE (2^56 <= q < 2^61): Harvey's butterflies with every lazy range doubled (forward
+//    [0,8q), inverse [0,4q); 8q < 2^64), which makes room for FAST's three-product quotient
+//    estimate (product in [0,4q)) in place of the exact 64x64 high half: one IMAD.WIDE less
+//    per butterfly than GENERIC for the 57..61-bit primes HE parameter sets like best.
+//
 //  SMALL (q < 2^30): 4q < 2^32, so every lazy value is ONE 32-bit word.  Same Harvey
 //    butterflies as GENERIC with beta = 2^32 (twiddle pairs {w, floor(w 2^32/q)}):
 //    one IMAD.WIDE + two IMADs per twiddle product instead of 6 + 4, conditional
@@ -69,7 +74,7 @@ namespace {
 //    work these kernels are HBM-bound.
 //  All modes produce the same canonical values; lazy outputs (out_mf 4 / 2)
 //  are congruent and inside the advertised range.
-enum : int { kGeneric = 0, kFast = 1, kSmall = 2 };
+enum : int { kGeneric = 0, kFast = 1, kSmall = 2, kWide = 3 };
 
 // element and twiddle types of a mode
 template <int MODE>
@@ -83,6 +88,7 @@ struct Ar<kSmall> {
   using Tw = Twiddle32;
 };
 constexpr u64 kFastModulusLimit = 1ull << 56;
+constexpr u64 kWideModulusLimit = 1ull << 61;
 constexpr int kFastProd = 4;   // FAST: a twiddle product is < 4q
 constexpr int kFastBound = 8;  // FAST inverse: every value is < 8q at a pass boundary
 
@@ -166,7 +172,7 @@ __device__ __forceinline__ u64 mad_chain(u64 x, u64 w, u64 Q, const Mod& m) {
 // x*w mod q, lazily: exact quotient -> [0,2q); approximate quotient -> [0,4q)
 template <int MODE>
 __device__ __forceinline__ u64 mul_tw(u64 x, const Twiddle w, const Mod& m) {
-  const u64 Q = MODE == kFast ? mulhi_approx(x, w.wp) : mulhi(x, w.wp);
+  const u64 Q = (MODE == kFast || MODE == kWide) ? mulhi_approx(x, w.wp) : mulhi(x, w.wp);
   return mad_chain(x, w.w, Q, m);
 }
 __device__ __forceinline__ u64 mul_tw_exact(u64 x, const Twiddle w, const Mod& m) {
@@ -200,6 +206,11 @@ __device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, const Twiddle w, const 
     const u64 T = mul_tw<kFast>(Y, w, m);  // [0,4q)
     Y = X + m.four_q - T;
     X = X + T;
+  } else if (MODE == kWide) {
+    const u64 tx = csub(X, m.four_q);      // [0,8q) -> [0,4q)
+    const u64 T = mul_tw<kWide>(Y, w, m);  // [0,4q)
+    X = tx + T;
+    Y = tx + m.four_q - T;
   } else {
     const u64 tx = csub(X, m.two_q);
     const u64 T = mul_tw<kGeneric>(Y, w, m);  // [0,2q)
@@ -215,6 +226,11 @@ __device__ __forceinline__ void inv_bfly(u64& X, u64& Y, const Twiddle w, const 
     const u64 d = X + cq - Y;
     X = X + Y;
     Y = mul_tw<kFast>(d, w, m);  // [0,4q)
+  } else if (MODE == kWide) {
+    const u64 s = X + Y;  // inputs in [0,4q)
+    const u64 d = X + m.four_q - Y;
+    X = csub(s, m.four_q);
+    Y = mul_tw<kWide>(d, w, m);  // [0,4q)
   } else {
     const u64 s = X + Y;
     const u64 d = X + m.two_q - Y;
@@ -240,6 +256,7 @@ __device__ __forceinline__ u64 fwd_out(u64 v, const Mod& m, int out_mf) {
     v = barrett_lazy_bigq(v, m);  // [0,2q), fine for out_mf == 4 as well
     return out_mf == 1 ? csub(v, m.q) : v;
   }
+  if (MODE == kWide) v = csub(v, m.four_q);  // [0,8q) -> [0,4q)
   return out_mf == 1 ? csub(csub(v, m.two_q), m.q) : v;
 }
 // inverse output after the folded root stage: [0,2q) -> [0,q) when out_mf == 1
@@ -301,6 +318,7 @@ __host__ __device__ constexpr int inv_stage_cover(int s) { return kFastBound << 
 template <int MODE>
 __device__ __forceinline__ typename Ar<MODE>::E stage_cq(int step, const Mod& m) {
   if (MODE == kFast) return (u64)inv_stage_cover(step) * m.q;
+  if (MODE == kWide) return m.four_q;
   return (typename Ar<MODE>::E)m.two_q;
 }
 
@@ -838,7 +856,9 @@ inline int pick_mode(u64 q) {
   static const bool force_generic = env_int("HEXL_B200_FORCE_GENERIC", 0) != 0;
   if (force_generic) return kGeneric;
   if (q < kSmallModulusLimit) return kSmall;
-  return (q < kFastModulusLimit && q >= (1ull << 32)) ? kFast : kGeneric;
+  if (q < kFastModulusLimit && q >= (1ull << 32)) return kFast;
+  static const bool no_wide = env_int("HEXL_B200_NO_WIDE", 0) != 0;
+  return (q >= kFastModulusLimit && q < kWideModulusLimit && !no_wide) ? kWide : kGeneric;
 }
 
 // the tables of a mode

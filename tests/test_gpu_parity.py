@@ -146,7 +146,8 @@ def test_ntt_extreme_inputs(hb, checker):
     largest modulus of each arithmetic mode: q just below 2^62 (GENERIC butterflies) and
     q just below 2^56 (FAST butterflies, where the lazy ranges come closest to 2^64),
     including N = 2^17 whose column pass runs 5 unreduced stages."""
-    for bits in (61, 55, 29):  # 29: q just below 2^30, 4q just below 2^32 (32-bit-word kernels)
+    # 60: q just below 2^61, 8q just below 2^64 (WIDE butterflies); 29: q just below 2^30 (32-bit-word kernels)
+    for bits in (61, 60, 55, 29):
         for logn in (4, 10, 12, 15, 17):
             n = 1 << logn
             q = hb.GeneratePrimes(1, bits, False, n)[0]  # largest primes below 2^(bits+1)

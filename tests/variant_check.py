@@ -26,7 +26,7 @@ def host(t):
 
 for logn in (12, 14, 15, 16, 17):
     n = 1 << logn
-    for bits in (29, 50, 61):
+    for bits in (29, 50, 60, 61):
         q = hb.GeneratePrimes(1, bits, True, n)[0]
         t = hb.NTT(n, q)
         batch = 5
