@@ -229,7 +229,7 @@ class NTT:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and _lib is not None:  # module globals are already gone at interpreter shutdown
             _lib.hexl_b200_ntt_release(h)
 
     @staticmethod
