@@ -224,6 +224,11 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
     torch.cuda.set_device(local)
+    # stdout is reserved for the one JSON line: libraries that print there (NCCL's version banner
+    # does) are sent to stderr at the file-descriptor level, the line goes to the saved descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = 1 << args.logn
@@ -341,14 +346,24 @@ def run_b200_arm(args):
     # ---- end to end through the host-pointer path of the C ABI
     e2e = None
     if not args.no_e2e:
-        eb = args.e2e_batch or batch
+        # per-GPU batch of the host-pointer leg: the full batch on one GPU; 2048 polynomials
+        # (1 GiB per pinned buffer, ~50 ms per step) per rank when several ranks pin host memory at once
+        eb = args.e2e_batch or (batch if world == 1 else min(batch, 2048))
         hx = hy = hz = None
         while eb >= 64:
             try:
                 hx, hy, hz = (hb.pinned_empty(n * eb) for _ in range(3))
                 break
             except hb.HexlB200Error:
+                hx = hy = hz = None
                 eb //= 2
+        # every rank must run the same number of units (and the same barriers): agree on the minimum
+        agreed = int(-max_over_ranks(-float(eb if hx is not None else 0), world))
+        if agreed < 64:
+            hx = None
+        elif agreed < eb:
+            eb = agreed
+            hx, hy, hz = hx[:n * eb], hy[:n * eb], hz[:n * eb]
         if hx is not None:
             rng = np.random.default_rng(7 + rank)
             hx[:] = rng.integers(0, q, size=n * eb, dtype=np.uint64)
@@ -371,8 +386,7 @@ def run_b200_arm(args):
                    "h2d_bytes_per_step": 2 * 8 * n * eb, "d2h_bytes_per_step": 2 * 8 * n * eb,
                    "batch_per_gpu": eb, "steps": esteps, "ms_per_step": 1e3 * dt / esteps,
                    "path": "hexl_b200_ntt_forward/inverse with pinned HOST pointers (library stages H2D/kernel/D2H in 32 MiB chunks on 3 streams)"}
-            for a in (hx, hy, hz):
-                hb.pinned_free(a)
+            # (pinned buffers are released at process exit)
 
     # ---- CPU baseline (rank 0, single-GPU runs only)
     cpu = None
@@ -395,7 +409,7 @@ def run_b200_arm(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "eltwise": elt,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
