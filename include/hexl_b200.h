@@ -1,6 +1,7 @@
 /* hexl_b200.h -- C ABI of libhexl_b200.so, the Blackwell (sm_100a) drop-in for the
- * intel/hexl hot path: NTT::ComputeForward / ComputeInverse and the seven
- * Eltwise*Mod operations.
+ * intel/hexl hot path: NTT::ComputeForward / ComputeInverse, the seven Eltwise*Mod
+ * operations, and the SEAL-shaped callers built on them (DyadicMultiply, KeySwitch,
+ * the NTT cache).
  *
  * Every entry point names the reference interface it replaces (file:line relative
  * to the intel/hexl v1.2.5 tree).  The C++ headers under include/hexl/ re-create
@@ -14,8 +15,10 @@
  *    storage; the call is enqueued on `stream` and returns without synchronising)
  *    or a HOST pointer (pageable or pinned; the call stages the buffers through
  *    the GPU -- H2D, kernel, D2H, chunked so copies and kernels overlap -- and
- *    returns when `result` is complete).  All data pointers of one call must be
- *    of the same kind.  `result` may alias an input (in place), as in the
+ *    returns when `result` is complete).  Unified-memory pointers
+ *    (hexl_b200_managed_alloc) are worked on in place like device pointers, and
+ *    with stream == NULL the call returns with the result complete.  All data
+ *    pointers of one call must be of the same kind.  `result` may alias an input (in place), as in the
  *    reference (test/test-ntt.cpp:240-243).
  *  - `stream` is a cudaStream_t passed as void*; NULL = the legacy default stream.
  *  - Batched calls take `batch` independent units laid out back to back
