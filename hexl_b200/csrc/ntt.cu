@@ -122,6 +122,58 @@ cudaError_t launch_fused(bool fwd, const NttDeviceTables& t, u64* result, const 
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// SMALL mode: the single kernel that keeps the intermediate in the cluster's shared memory
+template <int LOGR>
+cudaError_t launch_dsmem(bool fwd, const NttDeviceTables& t, u64* result, const u64* operand, u64 batch, int out_mf,
+                         cudaStream_t stream) {
+  using Cfg = DsmemCfg<LOGR>;
+  const Mod m = make_mod(t);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(batch * Cfg::K));
+  cfg.blockDim = dim3(Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = Cfg::K;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (fwd) {
+    if ((e = ensure_dynamic_smem<ntt_dsmem_fwd<LOGR>>(Cfg::SMEM)) != cudaSuccess) return e;
+    e = cudaLaunchKernelEx(&cfg, ntt_dsmem_fwd<LOGR>, result, operand, t.fwd32, m, out_mf);
+  } else {
+    if ((e = ensure_dynamic_smem<ntt_dsmem_inv<LOGR>>(Cfg::SMEM)) != cudaSuccess) return e;
+    e = cudaLaunchKernelEx(&cfg, ntt_dsmem_inv<LOGR>, result, operand, t.inv32, m, out_mf, t.inv_n32, t.inv_n_w32);
+  }
+  count_launch();
+  return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+cudaError_t launch_dsmem_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64* result, const u64* operand,
+                             u64 batch, int out_mf, cudaStream_t stream) {
+  switch (log_r) {
+    case 2: return launch_dsmem<2>(fwd, t, result, operand, batch, out_mf, stream);
+    case 3: return launch_dsmem<3>(fwd, t, result, operand, batch, out_mf, stream);
+    case 4: return launch_dsmem<4>(fwd, t, result, operand, batch, out_mf, stream);
+    case 5: return launch_dsmem<5>(fwd, t, result, operand, batch, out_mf, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// log2(N / 4096) for which the distributed-shared-memory kernel is used (SMALL mode); 0 = none.
+// Measured (2^28 coefficients, 29-bit q, forward / inverse ms): N = 2^14 1.34 / 1.15 vs 1.42 / 1.25 for
+// the L2 variant, 2^15 1.27 / 1.22 vs 1.33 / 1.28; with two or more rows per CTA it loses
+// (2^16 1.41 / 1.49 vs 1.34 / 1.42, 2^17 1.63 / 1.75 vs 1.38 / 1.53), so the default stops at 2^15
+// (HEXL_B200_DSMEM=2 forces it for every size, 0 disables it).
+int dsmem_log_r(int log_n) {
+  static const int mode = env_int("HEXL_B200_DSMEM", 1);
+  const int lr = log_n - DsmemCfg<2>::LOGC;
+  return (mode != 0 && lr >= 2 && lr <= (mode >= 2 ? 5 : 3)) ? lr : 0;
+}
+
 // log2(N / 4096) for which the single fused kernel is used; 0 = none
 template <int MODE>
 int fused_log_r(int log_n) {
@@ -145,6 +197,8 @@ cudaError_t launch_fused_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64*
 template <int MODE>
 cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
+  if constexpr (MODE == kSmall)
+    if (const int lr = dsmem_log_r(t.log_n)) return launch_dsmem_dyn(lr, true, t, result, operand, batch, out_mf, stream);
   if (const int lr = fused_log_r<MODE>(t.log_n)) return launch_fused_dyn<MODE>(lr, true, t, result, operand, batch, out_mf, stream);
   const int log_c = pick_row_log(t.log_n);
   int radices[8];
@@ -163,6 +217,8 @@ cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* opera
 template <int MODE>
 cudaError_t inverse_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
+  if constexpr (MODE == kSmall)
+    if (const int lr = dsmem_log_r(t.log_n)) return launch_dsmem_dyn(lr, false, t, result, operand, batch, out_mf, stream);
   if (const int lr = fused_log_r<MODE>(t.log_n)) return launch_fused_dyn<MODE>(lr, false, t, result, operand, batch, out_mf, stream);
   const int log_c = pick_row_log(t.log_n);
   int radices[8];

@@ -512,7 +512,7 @@ struct RowCfg {
 // Global-memory access policies for coefficients.  Streaming (evict-first) for
 // data touched once; L2 variants for the intermediate a fused kernel hands from
 // its column phase to its row phase (written by one CTA, read by another).
-enum : int { kStream = 0, kViaL2 = 1 };
+enum : int { kStream = 0, kViaL2 = 1, kSmemRow = 2 };  // kSmemRow: the "global" side is a row of E in shared memory
 template <int POLICY>
 __device__ __forceinline__ u64 ld_coef(const u64* p) {
   return POLICY == kViaL2 ? __ldcg(p) : __ldcs(p);
@@ -525,10 +525,26 @@ __device__ __forceinline__ void st_coef(u64* p, u64 v) {
     __stcs(p, v);
 }
 
+// coefficient idx of a row whose storage is global u64 (kStream / kViaL2) or a shared-memory row of E
+template <int POLICY, typename E>
+__device__ __forceinline__ E ld_row(const void* base, unsigned idx) {
+  if constexpr (POLICY == kSmemRow)
+    return static_cast<const E*>(base)[idx];
+  else
+    return (E)ld_coef<POLICY>(static_cast<const u64*>(base) + idx);
+}
+template <int POLICY, typename E>
+__device__ __forceinline__ void st_row(void* base, unsigned idx, E v) {
+  if constexpr (POLICY == kSmemRow)
+    static_cast<E*>(base)[idx] = v;
+  else
+    st_coef<POLICY>(static_cast<u64*>(base) + idx, v);
+}
+
 // Forward transform of one row of C = 2^LOGC contiguous coefficients rooted at
 // tree node `base`, by the T = C/16 threads whose index in the row is u.
 template <int MODE, int LOGC, int LD, int ST>
-__device__ __forceinline__ void row_fwd_body(u64* out, const u64* in, typename Ar<MODE>::E* srow, unsigned u,
+__device__ __forceinline__ void row_fwd_body(void* out, const void* in, typename Ar<MODE>::E* srow, unsigned u,
                                              u64 base, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod& m,
                                              int out_mf, bool active) {
   using E = typename Ar<MODE>::E;
@@ -537,7 +553,7 @@ __device__ __forceinline__ void row_fwd_body(u64* out, const u64* in, typename A
   constexpr int LB0 = LOGC - 4;  // pass 0: register bits are the top 4 index bits
   Tw* stab = reinterpret_cast<Tw*>(srow + (1 << LOGC));
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = (E)ld_coef<LD>(in + reg_index<LB0>(u, e));
+  for (int e = 0; e < 16; ++e) v[e] = ld_row<LD, E>(in, reg_index<LB0>(u, e));
   if constexpr (RowCfg<LOGC>::TW_TABLES) {
     load_row_twiddles<LOGC>(stab, u, base, tw);
     __syncthreads();
@@ -553,13 +569,13 @@ __device__ __forceinline__ void row_fwd_body(u64* out, const u64* in, typename A
   if constexpr (LOGC > 4) smem_exchange<0, LB_OUT>(v, srow, u);
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) st_coef<ST>(out + reg_index<LB_OUT>(u, e), v[e]);
+    for (int e = 0; e < 16; ++e) st_row<ST, E>(out, reg_index<LB_OUT>(u, e), v[e]);
   }
 }
 
 // Inverse transform of one row (the last log2 C ... first stages of the GS order).
 template <int MODE, int LOGC, int LD, int ST>
-__device__ __forceinline__ void row_inv_body(u64* out, const u64* in, typename Ar<MODE>::E* srow, unsigned u,
+__device__ __forceinline__ void row_inv_body(void* out, const void* in, typename Ar<MODE>::E* srow, unsigned u,
                                              u64 base, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod& m,
                                              int out_mf, bool fold, typename Ar<MODE>::Tw inv_n,
                                              typename Ar<MODE>::Tw inv_n_w, bool active) {
@@ -571,7 +587,7 @@ __device__ __forceinline__ void row_inv_body(u64* out, const u64* in, typename A
   constexpr int LB_IN = LB0 < 4 ? LB0 : 4;  // 16 lanes read one 128-byte line per instruction
   Tw* stab = reinterpret_cast<Tw*>(srow + (1 << LOGC));
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = (E)ld_coef<LD>(in + reg_index<LB_IN>(u, e));
+  for (int e = 0; e < 16; ++e) v[e] = ld_row<LD, E>(in, reg_index<LB_IN>(u, e));
   if constexpr (Cfg::TW_TABLES) {
     load_row_twiddles<LOGC>(stab, u, base, tw);
     __syncthreads();  // tables are filled by other warps than the ones that read them
@@ -583,7 +599,7 @@ __device__ __forceinline__ void row_inv_body(u64* out, const u64* in, typename A
   // only the kernel holding the root stage applies the output range
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) st_coef<ST>(out + reg_index<LB0>(u, e), fold ? inv_out(v[e], m, out_mf) : v[e]);
+    for (int e = 0; e < 16; ++e) st_row<ST, E>(out, reg_index<LB0>(u, e), fold ? inv_out(v[e], m, out_mf) : v[e]);
   }
 }
 
@@ -626,16 +642,14 @@ __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE
 // One column: R = 2^LOGR coefficients at stride 2^log_stride starting at `off`,
 // the first (forward) / last (inverse) LOGR stages of a sub-block whose R-1
 // twiddles stw[1..R-1] are laid out as a local tree (node 2^s + i).
-template <int MODE, int LOGR, bool FWD, int LD, int ST>
-__device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 off, int log_stride,
-                                         const typename Ar<MODE>::Tw* stw, const Mod& m, int out_mf, bool root_fold,
-                                         typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w) {
+// the register work of a column: LOGR stages on R values, twiddles from the local tree stw
+template <int MODE, int LOGR, bool FWD>
+__device__ __forceinline__ void col_stages(typename Ar<MODE>::E (&v)[1 << LOGR], const typename Ar<MODE>::Tw* stw,
+                                           const Mod& m, bool root_fold, typename Ar<MODE>::Tw inv_n,
+                                           typename Ar<MODE>::Tw inv_n_w) {
   using E = typename Ar<MODE>::E;
   using Tw = typename Ar<MODE>::Tw;
   constexpr int R = 1 << LOGR;
-  E v[R];
-#pragma unroll
-  for (int e = 0; e < R; ++e) v[e] = (E)ld_coef<LD>(operand + off + ((u64)e << log_stride));
 #pragma unroll
   for (int step = 0; step < LOGR; ++step) {
     const int s = FWD ? step : LOGR - 1 - step;      // stage inside the sub-block
@@ -659,10 +673,22 @@ __device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 of
       }
     }
   }
-  const bool final_out = !FWD && root_fold;
   if constexpr (!FWD && MODE == kFast) {
-    if (!final_out) inv_pass_fixup<LOGR, R>(v, m);
+    if (!root_fold) inv_pass_fixup<LOGR, R>(v, m);
   }
+}
+
+template <int MODE, int LOGR, bool FWD, int LD, int ST>
+__device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 off, int log_stride,
+                                         const typename Ar<MODE>::Tw* stw, const Mod& m, int out_mf, bool root_fold,
+                                         typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w) {
+  using E = typename Ar<MODE>::E;
+  constexpr int R = 1 << LOGR;
+  E v[R];
+#pragma unroll
+  for (int e = 0; e < R; ++e) v[e] = (E)ld_coef<LD>(operand + off + ((u64)e << log_stride));
+  col_stages<MODE, LOGR, FWD>(v, stw, m, root_fold, inv_n, inv_n_w);
+  const bool final_out = !FWD && root_fold;
 #pragma unroll
   for (int e = 0; e < R; ++e)
     st_coef<ST>(result + off + ((u64)e << log_stride), final_out ? inv_out(v[e], m, out_mf) : v[e]);
@@ -781,6 +807,123 @@ __global__ void __launch_bounds__(FusedCfg<LOGR, MODE>::THREADS, FusedCfg<LOGR, 
   for (int c = threadIdx.x; c < COLS; c += Cfg::THREADS)
     col_body<MODE, LOGR, false, kViaL2, kStream>(result, result, poly_off + rank * COLS + c, Cfg::LOGC, stw, m,
                                                  out_mf, true, inv_n, inv_n_w);
+}
+
+// ------------------------------------- fused kernels through distributed shared memory
+// SMALL mode only (32-bit words): the whole polynomial fits in the shared memory of its
+// cluster -- N * 4 bytes spread over K CTAs -- so the intermediate between the column phase
+// and the row phase never leaves the SMs.  CTA `rank` owns rows rank, rank + K, ... of the
+// R x 4096 matrix.  Forward: the column phase of every CTA scatters its results straight
+// into the owners' shared memory (st.shared::cluster, 128 contiguous bytes per warp and
+// row), one cluster barrier, then every CTA transforms its own rows from local shared
+// memory to HBM.  Inverse: rows first into local shared memory, barrier, the column phase
+// gathers from the owners (ld.shared::cluster), a last barrier keeps every CTA's memory
+// alive until its peers have read it.  HBM sees 8N bytes in and 8N bytes out, L2 nothing.
+__device__ __forceinline__ unsigned dsmem_address(const void* local_smem, unsigned cta_rank) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(local_smem);
+  unsigned r;
+  asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void dsmem_store(unsigned addr, unsigned v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned dsmem_load(unsigned addr) {
+  unsigned v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+template <int LOGR>
+struct DsmemCfg {
+  static constexpr int LOGC = 12, C = 1 << LOGC, R = 1 << LOGR;
+  static constexpr int K = R < 8 ? R : 8;            // CTAs per cluster
+  static constexpr int RPC = R / K;                  // rows owned by one CTA
+  static constexpr int THREADS = 256;
+  static constexpr int COLS = C / K;                 // columns one CTA runs in the column phase
+  // owned rows + exchange buffer (32-bit words) + the row kernel's twiddle tables
+  static constexpr size_t SMEM = (size_t)(RPC + 1) * C * sizeof(unsigned) + kRowTwEntries * sizeof(Twiddle32);
+  static constexpr int MIN_BLOCKS = SMEM <= 56 * 1024 ? 4 : (SMEM <= 75 * 1024 ? 3 : 2);
+};
+
+template <int LOGR>
+__global__ void __launch_bounds__(DsmemCfg<LOGR>::THREADS, DsmemCfg<LOGR>::MIN_BLOCKS)
+    ntt_dsmem_fwd(u64* result, const u64* operand, const Twiddle32* __restrict__ tw, const Mod m, int out_mf) {
+  using Cfg = DsmemCfg<LOGR>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned* rows = reinterpret_cast<unsigned*>(smem_raw);  // [RPC][C]
+  unsigned* xbuf = rows + Cfg::RPC * Cfg::C;               // exchange buffer, twiddle tables behind it
+  __shared__ Twiddle32 stw[Cfg::R];
+  const unsigned rank = blockIdx.x % Cfg::K;
+  const u64 poly_off = (u64)(blockIdx.x / Cfg::K) << (Cfg::LOGC + LOGR);
+  for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
+    if (l) stw[l] = ld_tw(tw + l);
+  __syncthreads();
+  // phase 1: my columns of every row -> the row owners' shared memory
+  unsigned owner_base[Cfg::K];
+#pragma unroll
+  for (int o = 0; o < Cfg::K; ++o) owner_base[o] = dsmem_address(rows, o);
+#pragma unroll 1
+  for (int c = threadIdx.x; c < Cfg::COLS; c += Cfg::THREADS) {
+    const unsigned col = rank * Cfg::COLS + c;
+    unsigned v[Cfg::R];
+#pragma unroll
+    for (int e = 0; e < Cfg::R; ++e) v[e] = (unsigned)ld_coef<kStream>(operand + poly_off + ((u64)e << Cfg::LOGC) + col);
+    col_stages<kSmall, LOGR, true>(v, stw, m, false, Twiddle32{}, Twiddle32{});
+#pragma unroll
+    for (int e = 0; e < Cfg::R; ++e)  // row e lives in CTA e % K, slot e / K
+      dsmem_store(owner_base[e % Cfg::K] + ((e / Cfg::K) * Cfg::C + col) * 4u, v[e]);
+  }
+  cluster_barrier();
+  // phase 2: my rows, shared memory -> HBM
+#pragma unroll 1
+  for (int lr = 0; lr < Cfg::RPC; ++lr) {
+    const unsigned r = rank + lr * Cfg::K;
+    row_fwd_body<kSmall, Cfg::LOGC, kSmemRow, kStream>(result + poly_off + (u64)r * Cfg::C, rows + lr * Cfg::C, xbuf,
+                                                       threadIdx.x, (u64)Cfg::R + r, tw, m, out_mf, true);
+    if (lr + 1 < Cfg::RPC) __syncthreads();  // the next row reuses the exchange buffer and tables
+  }
+}
+
+template <int LOGR>
+__global__ void __launch_bounds__(DsmemCfg<LOGR>::THREADS, DsmemCfg<LOGR>::MIN_BLOCKS)
+    ntt_dsmem_inv(u64* result, const u64* operand, const Twiddle32* __restrict__ tw, const Mod m, int out_mf,
+                  Twiddle32 inv_n, Twiddle32 inv_n_w) {
+  using Cfg = DsmemCfg<LOGR>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned* rows = reinterpret_cast<unsigned*>(smem_raw);
+  unsigned* xbuf = rows + Cfg::RPC * Cfg::C;
+  __shared__ Twiddle32 stw[Cfg::R];
+  const unsigned rank = blockIdx.x % Cfg::K;
+  const u64 poly_off = (u64)(blockIdx.x / Cfg::K) << (Cfg::LOGC + LOGR);
+  for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
+    if (l) stw[l] = ld_tw(tw + l);
+  // phase 1: my rows, HBM -> local shared memory (the barriers inside publish stw as well)
+#pragma unroll 1
+  for (int lr = 0; lr < Cfg::RPC; ++lr) {
+    const unsigned r = rank + lr * Cfg::K;
+    row_inv_body<kSmall, Cfg::LOGC, kStream, kSmemRow>(rows + lr * Cfg::C, operand + poly_off + (u64)r * Cfg::C, xbuf,
+                                                       threadIdx.x, (u64)Cfg::R + r, tw, m, out_mf, false, inv_n,
+                                                       inv_n_w, true);
+    __syncthreads();
+  }
+  cluster_barrier();
+  // phase 2: my columns gathered from the row owners, root stage folded with N^-1, -> HBM
+  unsigned owner_base[Cfg::K];
+#pragma unroll
+  for (int o = 0; o < Cfg::K; ++o) owner_base[o] = dsmem_address(rows, o);
+#pragma unroll 1
+  for (int c = threadIdx.x; c < Cfg::COLS; c += Cfg::THREADS) {
+    const unsigned col = rank * Cfg::COLS + c;
+    unsigned v[Cfg::R];
+#pragma unroll
+    for (int e = 0; e < Cfg::R; ++e) v[e] = dsmem_load(owner_base[e % Cfg::K] + ((e / Cfg::K) * Cfg::C + col) * 4u);
+    col_stages<kSmall, LOGR, false>(v, stw, m, true, inv_n, inv_n_w);
+#pragma unroll
+    for (int e = 0; e < Cfg::R; ++e)
+      st_coef<kStream>(result + poly_off + ((u64)e << Cfg::LOGC) + col, inv_out(v[e], m, out_mf));
+  }
+  cluster_barrier();  // nobody leaves while a peer may still read its rows
 }
 
 // --------------------------------------------------------- tiny-N stage kernel

@@ -168,13 +168,15 @@ def test_ntt_extreme_inputs(hb, checker):
                     assert (got < np.uint64(2 * q)).all()
 
 
-@pytest.mark.parametrize("env", [{"HEXL_B200_FUSED": "1", "HEXL_B200_FUSED_SMALL": "1"},
-                                 {"HEXL_B200_FUSED": "0", "HEXL_B200_FUSED_SMALL": "0"},
-                                 {"HEXL_B200_FORCE_GENERIC": "1"}])
+@pytest.mark.parametrize("env", [{"HEXL_B200_DSMEM": "2"},
+                                 {"HEXL_B200_FUSED": "1", "HEXL_B200_FUSED_SMALL": "1", "HEXL_B200_DSMEM": "0"},
+                                 {"HEXL_B200_FUSED": "0", "HEXL_B200_FUSED_SMALL": "0", "HEXL_B200_DSMEM": "0"},
+                                 {"HEXL_B200_FORCE_GENERIC": "1", "HEXL_B200_NO_WIDE": "1"}])
 def test_ntt_kernel_variants(env):
-    """The launch-time knobs are read once per process, so every variant (single fused
-    cluster kernel per transform, two-kernel split, GENERIC arithmetic for every modulus)
-    is checked against the oracle in its own process: tests/variant_check.py."""
+    """The launch-time knobs are read once per process, so every variant (distributed-shared-
+    memory kernel for small moduli, single fused cluster kernel per transform through L2,
+    two-kernel split, GENERIC arithmetic for every modulus) is checked against the oracle
+    in its own process: tests/variant_check.py."""
     import os
     import subprocess
     import sys
