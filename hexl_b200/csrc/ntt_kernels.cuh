@@ -368,9 +368,9 @@ struct PassTw {
 };
 
 template <int LOGC, typename Tw>
-__device__ __forceinline__ void load_row_twiddles(Tw* stab, unsigned u, u64 base, const Tw* __restrict__ tw) {
-  constexpr int T = (1 << LOGC) / 16;
-  for (int idx = u; idx < kRowTwEntries; idx += T) {
+__device__ __forceinline__ void load_row_twiddles(Tw* stab, unsigned tid, unsigned nthreads, u64 base,
+                                                  const Tw* __restrict__ tw) {
+  for (int idx = tid; idx < kRowTwEntries; idx += nthreads) {
     const int l = idx & 15;
     if (l == 0) continue;
     const u64 root = idx < 16 ? base : (base << 4) + ((idx - 16) >> 4);
@@ -546,16 +546,21 @@ __device__ __forceinline__ void st_row(void* base, unsigned idx, E v) {
 template <int MODE, int LOGC, int LD, int ST>
 __device__ __forceinline__ void row_fwd_body(void* out, const void* in, typename Ar<MODE>::E* srow, unsigned u,
                                              u64 base, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod& m,
-                                             int out_mf, bool active) {
+                                             int out_mf, bool active, typename Ar<MODE>::Tw* cta_stab = nullptr) {
   using E = typename Ar<MODE>::E;
   using Tw = typename Ar<MODE>::Tw;
   E v[16];
   constexpr int LB0 = LOGC - 4;  // pass 0: register bits are the top 4 index bits
-  Tw* stab = reinterpret_cast<Tw*>(srow + (1 << LOGC));
+  // cta_stab: every row of this CTA has the same root (whole polynomials, N == C): one table
+  // filled by all threads of the CTA instead of one per row
+  Tw* stab = cta_stab ? cta_stab : reinterpret_cast<Tw*>(srow + (1 << LOGC));
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = ld_row<LD, E>(in, reg_index<LB0>(u, e));
   if constexpr (RowCfg<LOGC>::TW_TABLES) {
-    load_row_twiddles<LOGC>(stab, u, base, tw);
+    if (cta_stab)
+      load_row_twiddles<LOGC>(stab, threadIdx.x, blockDim.x, base, tw);
+    else
+      load_row_twiddles<LOGC>(stab, u, (1u << LOGC) / 16, base, tw);
     __syncthreads();
   }
   reg_stages<MODE, LOGC, LB0, LOGC - 1, LB0, true>(v, u, base, tw, stab, m, false, Tw{}, Tw{});
@@ -578,18 +583,22 @@ template <int MODE, int LOGC, int LD, int ST>
 __device__ __forceinline__ void row_inv_body(void* out, const void* in, typename Ar<MODE>::E* srow, unsigned u,
                                              u64 base, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod& m,
                                              int out_mf, bool fold, typename Ar<MODE>::Tw inv_n,
-                                             typename Ar<MODE>::Tw inv_n_w, bool active) {
+                                             typename Ar<MODE>::Tw inv_n_w, bool active,
+                                             typename Ar<MODE>::Tw* cta_stab = nullptr) {
   using Cfg = RowCfg<LOGC>;
   using E = typename Ar<MODE>::E;
   using Tw = typename Ar<MODE>::Tw;
   E v[16];
   constexpr int LB0 = LOGC - 4;
   constexpr int LB_IN = LB0 < 4 ? LB0 : 4;  // 16 lanes read one 128-byte line per instruction
-  Tw* stab = reinterpret_cast<Tw*>(srow + (1 << LOGC));
+  Tw* stab = cta_stab ? cta_stab : reinterpret_cast<Tw*>(srow + (1 << LOGC));
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = ld_row<LD, E>(in, reg_index<LB_IN>(u, e));
   if constexpr (Cfg::TW_TABLES) {
-    load_row_twiddles<LOGC>(stab, u, base, tw);
+    if (cta_stab)
+      load_row_twiddles<LOGC>(stab, threadIdx.x, blockDim.x, base, tw);
+    else
+      load_row_twiddles<LOGC>(stab, u, (1u << LOGC) / 16, base, tw);
     __syncthreads();  // tables are filled by other warps than the ones that read them
   }
   // -> 16 consecutive coefficients per thread (warp-local exchange)
@@ -615,9 +624,14 @@ __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE
   const bool active = row < total_rows;
   if (!active) row = total_rows - 1;  // keep barriers uniform; stores are masked
   const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
+  typename Cfg::Tw* cta_stab = nullptr;  // whole polynomials per row: all rows of the CTA share root node 1
+  // (SMALL mode only: +5 % there; in the 64-bit modes the run-time table address costs more than the loads save)
+  if (MODE == kSmall && Cfg::ROWS > 1 && Cfg::TW_TABLES && rows_per_poly == 1)
+    cta_stab = reinterpret_cast<typename Cfg::Tw*>(smem + (size_t)Cfg::C * sizeof(typename Cfg::E));
   row_fwd_body<MODE, LOGC, kStream, kStream>(
       result + row * Cfg::C, operand + row * Cfg::C,
-      reinterpret_cast<typename Cfg::E*>(smem + (size_t)row_local * Cfg::ROW_BYTES), u, base, tw, m, out_mf, active);
+      reinterpret_cast<typename Cfg::E*>(smem + (size_t)row_local * Cfg::ROW_BYTES), u, base, tw, m, out_mf, active,
+      cta_stab);
 }
 
 template <int MODE, int LOGC>
@@ -632,10 +646,14 @@ __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE
   const bool active = row < total_rows;
   if (!active) row = total_rows - 1;
   const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
+  typename Cfg::Tw* cta_stab = nullptr;
+  // (SMALL mode only: +5 % there; in the 64-bit modes the run-time table address costs more than the loads save)
+  if (MODE == kSmall && Cfg::ROWS > 1 && Cfg::TW_TABLES && rows_per_poly == 1)
+    cta_stab = reinterpret_cast<typename Cfg::Tw*>(smem + (size_t)Cfg::C * sizeof(typename Cfg::E));
   row_inv_body<MODE, LOGC, kStream, kStream>(
       result + row * Cfg::C, operand + row * Cfg::C,
       reinterpret_cast<typename Cfg::E*>(smem + (size_t)row_local * Cfg::ROW_BYTES), u, base, tw, m, out_mf,
-      fold != 0, inv_n, inv_n_w, active);
+      fold != 0, inv_n, inv_n_w, active, cta_stab);
 }
 
 // ------------------------------------------------------------- column kernel
