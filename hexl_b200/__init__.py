@@ -94,6 +94,8 @@ _sig("hexl_b200_ntt_forward", _int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_ntt_inverse", _int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_ntt_forward_multi", _int, [C.POINTER(_vp), _u64, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_ntt_inverse_multi", _int, [C.POINTER(_vp), _u64, _vp, _vp, _u64, _u64, _u64, _vp])
+_sig("hexl_b200_eltwise_mult_mod_multi", _int, [_vp, _vp, _vp, _u64, _vp, _u64, _u64, _vp])
+_sig("hexl_b200_poly_multiply_multi", _int, [C.POINTER(_vp), _u64, _vp, _vp, _vp, _u64, _vp])
 _sig("hexl_b200_eltwise_add_mod", _int, [_vp, _vp, _vp, _u64, _u64, _vp])
 _sig("hexl_b200_eltwise_add_mod_scalar", _int, [_vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_eltwise_sub_mod", _int, [_vp, _vp, _vp, _u64, _u64, _vp])
@@ -291,6 +293,26 @@ def ComputeInverseMulti(ntts, result, operand, input_mod_factor=1, output_mod_fa
                         stream=None):
     return _multi(_lib.hexl_b200_ntt_inverse_multi, ntts, result, operand, input_mod_factor, output_mod_factor,
                   batch_per_modulus, stream)
+
+
+def EltwiseMultModMulti(result, operand1, operand2, n_per_modulus, moduli, input_mod_factor=1, stream=None):
+    """EltwiseMultMod over an RNS batch in one launch: block e (n_per_modulus elements) under moduli[e]"""
+    mods = np.ascontiguousarray(moduli, dtype=np.uint64)
+    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1); bp, _, _ = _buf(operand2)
+    _check(_lib.hexl_b200_eltwise_mult_mod_multi(rp, ap, bp, n_per_modulus, mods.ctypes.data, mods.size,
+                                                 input_mod_factor, _stream(stream, rc or ac)))
+    return result
+
+
+def PolyMultiplyMulti(ntts, result, a, b, batch_per_modulus=None, stream=None):
+    """Negacyclic products InvNTT(FwdNTT(a) .* FwdNTT(b)), polynomial u under ntts[u // batch_per_modulus]"""
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(a); bp, _, _ = _buf(b)
+    n = ntts[0].GetDegree()
+    if batch_per_modulus is None:
+        batch_per_modulus = an // (n * len(ntts))
+    hs = (_vp * len(ntts))(*[t._h for t in ntts])
+    _check(_lib.hexl_b200_poly_multiply_multi(hs, len(ntts), rp, ap, bp, batch_per_modulus, _stream(stream, rc or ac)))
+    return result
 
 
 # ---------------------------------------------------------------- element-wise

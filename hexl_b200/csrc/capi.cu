@@ -688,7 +688,6 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
   return 0;  // asynchronous on s; ~Scratch returns the buffers to the pool in stream order
 }
 
-constexpr u64 kFastLo = 1ull << 32, kFastHi = 1ull << 56;  // moduli eligible for the FAST butterflies (ntt_kernels.cuh)
 
 // `count` handles x `group` polynomials each, device pointers on device `dev`, in blocks of kParamBlock handles
 int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
@@ -698,16 +697,17 @@ int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, ui
     const uint64_t cnt = std::min<uint64_t>(kParamBlock, count - first);
     NttMulti multi{};
     multi.group = (unsigned)group;
-    bool all_fast = true;
+    uint64_t min_q = ~0ull, max_q = 0;
     for (uint64_t i = 0; i < cnt; ++i) {
       NttDeviceTables t;
       if (int rc = device_tables(handles[first + i], dev, &t)) return rc;
       multi.p[i] = t.dparams;
-      all_fast = all_fast && t.q >= kFastLo && t.q < kFastHi;
+      min_q = std::min(min_q, t.q);
+      max_q = std::max(max_q, t.q);
     }
     const uint64_t off = first * group * n;
-    cudaError_t e = launch_ntt_multi(forward, multi, handles[0]->log_n, all_fast, result + off, operand + off, out_mf,
-                                     cnt * group, s);
+    cudaError_t e = launch_ntt_multi(forward, multi, handles[0]->log_n, min_q, max_q, result + off, operand + off,
+                                     out_mf, cnt * group, s);
     if (e != cudaSuccess) return cuda_fail(e, "multi-modulus NTT launch");
   }
   return 0;
@@ -1052,6 +1052,107 @@ int hexl_b200_eltwise_cmp_sub_mod(uint64_t* result, const uint64_t* op1, uint64_
 int hexl_b200_ntt_get_cached(hexl_b200_ntt** out, uint64_t degree, uint64_t q) {
   if (!out) return fail(HEXL_B200_ERR_INVALID_ARG, "out == nullptr");
   return cached_ntt(out, degree, q);
+}
+
+// device side of EltwiseMultMod over an RNS batch
+static int rns_mult_on_device(uint64_t* result, const uint64_t* a, const uint64_t* b, uint64_t per_mod,
+                              const uint64_t* moduli, uint64_t num_moduli, int in_mf, cudaStream_t s) {
+  for (uint64_t first = 0; first < num_moduli; first += kParamBlock) {
+    const uint64_t count = std::min<uint64_t>(kParamBlock, num_moduli - first);
+    DyadicModuli mods;
+    for (uint64_t i = 0; i < count; ++i) mods.m[i] = dyadic_modulus(moduli[first + i]);
+    const uint64_t off = first * per_mod;
+    cudaError_t e = launch_rns_mult(result + off, a + off, b + off, per_mod, count, in_mf, mods, s);
+    if (e != cudaSuccess) return cuda_fail(e, "EltwiseMultMod (RNS batch) launch");
+  }
+  return 0;
+}
+
+int hexl_b200_eltwise_mult_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                                     uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli,
+                                     uint64_t in_mf, void* stream) {
+  // eltwise-mult-mod.cpp:23-36, per modulus
+  REQUIRE(result && operand1 && operand2 && moduli, "Require result, operand1, operand2, moduli != nullptr");
+  REQUIRE(n_per_modulus != 0 && num_moduli != 0, "Require n != 0");
+  REQUIRE(in_mf == 1 || in_mf == 2 || in_mf == 4, "Require input_mod_factor = 1, 2, or 4");
+  for (uint64_t i = 0; i < num_moduli; ++i)
+    REQUIRE(moduli[i] > 1 && moduli[i] < (1ull << 62) && moduli[i] * in_mf < (1ull << 63),
+            "Require 1 < modulus < 2^62 and input_mod_factor * modulus < 2^63");
+  PtrInfo pi;
+  if (int rc = classify_all({result, operand1, operand2}, &pi)) return rc;
+  const uint64_t total = n_per_modulus * num_moduli;
+  if (pi.where == Where::Device) {
+    DeviceGuard g;
+    if (int rc = g.enter(pi.device)) return rc;
+    for (uint64_t i = 0; i < num_moduli; ++i) {
+      if (int rc = check_bounds(operand1 + i * n_per_modulus, n_per_modulus, moduli[i] * in_mf, pi, "operand1")) return rc;
+      if (int rc = check_bounds(operand2 + i * n_per_modulus, n_per_modulus, moduli[i] * in_mf, pi, "operand2")) return rc;
+    }
+    if (int rc = rns_mult_on_device(result, operand1, operand2, n_per_modulus, moduli, num_moduli, (int)in_mf,
+                                    (cudaStream_t)stream))
+      return rc;
+    return finish_device_call(pi, stream);
+  }
+  Scratch ws(nullptr);  // host pointers: staged whole, synchronous
+  uint64_t *d1 = nullptr, *d2 = nullptr;
+  if (int rc = ws.get(&d1, total)) return rc;
+  if (int rc = ws.get(&d2, total)) return rc;
+  CU(cudaMemcpyAsync(d1, operand1, total * 8, cudaMemcpyHostToDevice, nullptr));
+  CU(cudaMemcpyAsync(d2, operand2, total * 8, cudaMemcpyHostToDevice, nullptr));
+  if (int rc = rns_mult_on_device(d1, d1, d2, n_per_modulus, moduli, num_moduli, (int)in_mf, nullptr)) return rc;
+  CU(cudaMemcpy(result, d1, total * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// FwdNTT(a), FwdNTT(b) (lazy outputs), point-wise product, InvNTT: all moduli per launch
+static int poly_multiply_on_device(int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
+                                   const uint64_t* a, const uint64_t* b, uint64_t group, cudaStream_t s) {
+  const uint64_t n = handles[0]->n, total = count * group * n;
+  if (result == b) std::swap(a, b);  // the product commutes; keep the in-place transform on `result`
+  Scratch ws(s);
+  uint64_t* fb = nullptr;
+  if (int rc = ws.get(&fb, total)) return rc;
+  std::vector<uint64_t> moduli(count);
+  for (uint64_t i = 0; i < count; ++i) moduli[i] = handles[i]->q;
+  if (int rc = ntt_multi_on_device(true, dev, handles, count, result, a, 4, group, s)) return rc;
+  if (int rc = ntt_multi_on_device(true, dev, handles, count, fb, b, 4, group, s)) return rc;
+  if (int rc = rns_mult_on_device(result, result, fb, group * n, moduli.data(), count, 4, s)) return rc;
+  return ntt_multi_on_device(false, dev, handles, count, result, result, 1, group, s);
+}
+
+int hexl_b200_poly_multiply_multi(hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result, const uint64_t* a,
+                                  const uint64_t* b, uint64_t group, void* stream) {
+  REQUIRE(handles && result && a && b, "Require handles, result, a, b != nullptr");
+  if (count == 0 || group == 0) return 0;
+  for (uint64_t i = 0; i < count; ++i) {
+    REQUIRE(handles[i] != nullptr, "Require handles[i] != nullptr");
+    REQUIRE(handles[i]->n == handles[0]->n, "all handles must share one degree");
+    REQUIRE(handles[i]->q < (1ull << 61), "Require modulus < 2^61 (lazy transform outputs feed the product)");
+  }
+  PtrInfo pi;
+  if (int rc = classify_all({result, a, b}, &pi)) return rc;
+  const uint64_t n = handles[0]->n, total = count * group * n;
+  if (pi.where == Where::Device) {
+    DeviceGuard g;
+    if (int rc = g.enter(pi.device)) return rc;
+    for (uint64_t i = 0; i < count; ++i) {
+      if (int rc = check_bounds(a + i * group * n, group * n, handles[i]->q, pi, "a")) return rc;
+      if (int rc = check_bounds(b + i * group * n, group * n, handles[i]->q, pi, "b")) return rc;
+    }
+    if (int rc = poly_multiply_on_device(pi.device, handles, count, result, a, b, group, (cudaStream_t)stream)) return rc;
+    return finish_device_call(pi, stream);
+  }
+  int cur = 0;
+  CU(cudaGetDevice(&cur));
+  Scratch ws(nullptr);
+  uint64_t *d1 = nullptr, *d2 = nullptr;
+  if (int rc = ws.get(&d1, total)) return rc;
+  if (int rc = ws.get(&d2, total)) return rc;
+  CU(cudaMemcpyAsync(d1, a, total * 8, cudaMemcpyHostToDevice, nullptr));
+  CU(cudaMemcpyAsync(d2, b, total * 8, cudaMemcpyHostToDevice, nullptr));
+  if (int rc = poly_multiply_on_device(cur, handles, count, d1, d1, d2, group, nullptr)) return rc;
+  CU(cudaMemcpy(result, d1, total * 8, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int hexl_b200_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2, uint64_t n,

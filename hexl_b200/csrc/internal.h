@@ -76,7 +76,8 @@ struct NttMulti {
   const NttDeviceParams* p[kParamBlock];
   unsigned group;
 };
-cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, bool all_fast, u64* result,
+// max_q = the largest modulus of the call: it selects the butterflies every entry can run
+cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, u64 min_q, u64 max_q, u64* result,
                              const u64* operand, int out_mf, u64 units, cudaStream_t stream);
 
 // ----------------------------------------------------- SEAL-shaped composites
@@ -95,6 +96,10 @@ struct KeyPointers {
 // moduli [first, first + count) of a DyadicMultiply over `num_moduli` moduli
 cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli, u64 first,
                                    u64 count, const DyadicModuli& mods, cudaStream_t stream);
+// EltwiseMultMod of `count` blocks of per_mod elements, block e under mods.m[e]; inputs < in_mf * q
+cudaError_t launch_rns_mult(u64* result, const u64* a, const u64* b, u64 per_mod, u64 count, int in_mf,
+                            const DyadicModuli& mods, cudaStream_t stream);
+
 // KeySwitch glue, batched over the RNS moduli of one parameter block (entry e of `mods`
 // describes modulus i0 + e).  KsModulus.a/b/c mean, per kernel:
 //   reduce: -            mac: a,b = 2^64 mod q and its Shoup factor, c = slot of q in the key

@@ -187,7 +187,7 @@ cudaError_t multi_impl(bool fwd, const NttMulti& multi, int log_n, u64* result, 
 
 }  // namespace
 
-cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, bool all_fast, u64* result,
+cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, u64 min_q, u64 max_q, u64* result,
                              const u64* operand, int out_mf, u64 units, cudaStream_t stream) {
   if (units == 0) return cudaSuccess;
   if (log_n < 4) {
@@ -199,9 +199,15 @@ cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, boo
     count_launch();
     return cudaGetLastError();
   }
+  // FAST needs every modulus in [2^32, 2^56), WIDE every modulus below 2^61 (its doubled lazy ranges
+  // are valid for any smaller q as well), GENERIC runs everything
   static const bool force_generic = env_int("HEXL_B200_FORCE_GENERIC", 0) != 0;
-  return (all_fast && !force_generic) ? multi_impl<kFast>(forward, multi, log_n, result, operand, out_mf, units, stream)
-                                      : multi_impl<kGeneric>(forward, multi, log_n, result, operand, out_mf, units, stream);
+  static const bool no_wide = env_int("HEXL_B200_NO_WIDE", 0) != 0;
+  if (!force_generic && min_q >= (1ull << 32) && max_q < kFastModulusLimit)
+    return multi_impl<kFast>(forward, multi, log_n, result, operand, out_mf, units, stream);
+  if (!force_generic && !no_wide && max_q < kWideModulusLimit)
+    return multi_impl<kWide>(forward, multi, log_n, result, operand, out_mf, units, stream);
+  return multi_impl<kGeneric>(forward, multi, log_n, result, operand, out_mf, units, stream);
 }
 
 }  // namespace hexl_b200

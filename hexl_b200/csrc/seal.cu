@@ -79,6 +79,36 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+// ---- EltwiseMultMod over an RNS batch: block e of per_mod elements under modulus e
+// (eltwise-mult-mod-internal.hpp:33-101 per element; inputs < in_mf * q_e, in_mf in {1,2,4}).
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+    rns_mult_kernel(u64* result, const u64* a, const u64* b, u64 per_mod, u64 count, int in_mf,
+                    const __grid_constant__ DyadicModuli mods) {
+  const u64 total = per_mod * count / VEC;
+  const u64 stride = (u64)gridDim.x * kThreads;
+  for (u64 i = (u64)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
+    const DyadicModulus& dm = mods.m[i * VEC / per_mod];
+    const MulCtx c{dm.q, dm.mu, dm.shift};
+    const Slots<VEC> x = ld_slots<VEC>(a + i * VEC), y = ld_slots<VEC>(b + i * VEC);
+    Slots<VEC> r;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      u64 xv = x.v[k], yv = y.v[k];
+      if (in_mf >= 4) {
+        xv = csub(xv, c.q << 1);
+        yv = csub(yv, c.q << 1);
+      }
+      if (in_mf >= 2) {
+        xv = csub(xv, c.q);
+        yv = csub(yv, c.q);
+      }
+      r.v[k] = mulmod(xv, yv, c);
+    }
+    st_slots<VEC>(result + i * VEC, r);
+  }
+}
+
 // ---- KeySwitch glue (key-switch-internal.cpp:60-198), every kernel batched over the RNS
 // moduli of one parameter block; layouts are [modulus][component or digit][n].
 
@@ -176,6 +206,25 @@ cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, 
     dyadic_kernel<2><<<(unsigned)blocks, kThreads, 0, stream>>>(result, op1, op2, n, num_moduli, first, count, mods);
   else
     dyadic_kernel<1><<<(unsigned)blocks, kThreads, 0, stream>>>(result, op1, op2, n, num_moduli, first, count, mods);
+  count_launch();
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rns_mult(u64* result, const u64* a, const u64* b, u64 per_mod, u64 count, int in_mf,
+                            const DyadicModuli& mods, cudaStream_t stream) {
+  const u64 total = per_mod * count;
+  if (total == 0) return cudaSuccess;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const bool vec = per_mod % 2 == 0 &&
+                   ((reinterpret_cast<uintptr_t>(result) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  u64 blocks = blocks_for(vec ? total / 2 : total);
+  if (blocks > (u64)sms * 16) blocks = (u64)sms * 16;
+  if (vec)
+    rns_mult_kernel<2><<<(unsigned)blocks, kThreads, 0, stream>>>(result, a, b, per_mod, count, in_mf, mods);
+  else
+    rns_mult_kernel<1><<<(unsigned)blocks, kThreads, 0, stream>>>(result, a, b, per_mod, count, in_mf, mods);
   count_launch();
   return cudaGetLastError();
 }

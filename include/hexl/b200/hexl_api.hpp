@@ -368,6 +368,16 @@ class NTT {
                                                    output_mod_factor, batch_per_modulus, stream));
   }
 
+  // result = InvNTT(FwdNTT(a) .* FwdNTT(b)) for count * batch_per_modulus polynomials (negacyclic
+  // products, polynomial u under ntts[u / batch_per_modulus]): the FwdNTT -> EltwiseMultMod -> InvNTT
+  // pipeline as one call and a handful of launches.
+  static void PolyMultiplyMulti(const NTT* const* ntts, size_t count, uint64_t* result, const uint64_t* a,
+                                const uint64_t* b, uint64_t batch_per_modulus = 1, void* stream = nullptr) {
+    std::vector<hexl_b200_ntt*> hs(count);
+    for (size_t i = 0; i < count; ++i) hs[i] = ntts[i]->m_handle;
+    b200_detail::Throw(hexl_b200_poly_multiply_multi(hs.data(), count, result, a, b, batch_per_modulus, stream));
+  }
+
   uint64_t GetMinimalRootOfUnity() const { return hexl_b200_ntt_minimal_root(m_handle); }
   uint64_t GetDegree() const { return hexl_b200_ntt_degree(m_handle); }
   uint64_t GetModulus() const { return hexl_b200_ntt_modulus(m_handle); }

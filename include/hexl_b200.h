@@ -140,6 +140,20 @@ int hexl_b200_ntt_inverse_multi(hexl_b200_ntt* const* handles, uint64_t count, u
                                 const uint64_t* operand, uint64_t input_mod_factor,
                                 uint64_t output_mod_factor, uint64_t batch_per_modulus, void* stream);
 
+/* The other two steps of an RNS polynomial product, with the same batching (not in the
+ * reference, whose callers loop over the moduli: dyadic-multiply-internal.cpp:50-72):
+ * EltwiseMultMod (eltwise-mult-mod.hpp:23) over `num_moduli` blocks of n_per_modulus
+ * elements, block e under moduli[e], in one launch;  and the whole negacyclic product
+ * result = InvNTT(FwdNTT(a) .* FwdNTT(b)) of count * batch_per_modulus polynomials,
+ * polynomial u under handles[u / batch_per_modulus] (BASELINE configs[3]: FwdNTT ->
+ * EltwiseMultMod -> InvNTT), 4 to 6 launches whatever `count`.  Inputs < q, outputs
+ * in [0, q); result may be a, b or a separate buffer. */
+int hexl_b200_eltwise_mult_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                                     uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli,
+                                     uint64_t input_mod_factor, void* stream);
+int hexl_b200_poly_multiply_multi(hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
+                                  const uint64_t* a, const uint64_t* b, uint64_t batch_per_modulus, void* stream);
+
 /* ---- element-wise operations (hexl/include/hexl/eltwise/ *.hpp) -------------------
  * n = number of elements (for batched use pass n = batch * N: the ops are
  * position-independent). */

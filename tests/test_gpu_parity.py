@@ -237,6 +237,43 @@ def test_multi_modulus_launch_matches_oracle(hb, checker, logn, group):
         assert (y == exp_f).all()
 
 
+@pytest.mark.parametrize("logn,group,nmods", [(3, 2, 3), (8, 3, 5), (12, 2, 4), (15, 1, 3), (7, 1, 70)])
+def test_rns_product_pipeline_matches_oracle(hb, checker, logn, group, nmods):
+    """hexl_b200_eltwise_mult_mod_multi and hexl_b200_poly_multiply_multi against the oracle's
+    FwdNTT -> EltwiseMultMod -> InvNTT per modulus (BASELINE configs[3]); result separate,
+    aliasing a, aliasing b; device and host pointers."""
+    n = 1 << logn
+    bits = [max(logn + 2, 20), 50, 60, 40, 29][:min(nmods, 5)]
+    mods = [hb.GeneratePrimes(1, bb, True, n)[0] for bb in bits]
+    if nmods > 5:
+        mods += [q for q in hb.GeneratePrimes(nmods, 45, True, n) if q not in mods][:nmods - 5]
+    ntts = [hb.NTT(n, q) for q in mods]
+    sz = n * group
+    a = np.concatenate([uniform_below(3 * i + 1, sz, q) for i, q in enumerate(mods)])
+    b = np.concatenate([uniform_below(3 * i + 2, sz, q) for i, q in enumerate(mods)])
+    prod = np.concatenate([checker.mult_mod(a[i * sz:(i + 1) * sz], b[i * sz:(i + 1) * sz], q) for i, q in enumerate(mods)])
+    o = dev(np.zeros_like(a))
+    hb.EltwiseMultModMulti(o, dev(a), dev(b), sz, mods)
+    assert (host(o) == prod).all()
+    h = np.zeros_like(a)
+    hb.EltwiseMultModMulti(h, a, b, sz, mods)
+    assert (h == prod).all()
+    conv = np.concatenate([
+        checker.ntt_inverse(checker.mult_mod(checker.ntt_forward(a[i * sz:(i + 1) * sz], n, q),
+                                             checker.ntt_forward(b[i * sz:(i + 1) * sz], n, q), q), n, q)
+        for i, q in enumerate(mods)])
+    da, db = dev(a), dev(b)
+    hb.PolyMultiplyMulti(ntts, o, da, db, group)
+    assert (host(o) == conv).all() and (host(da) == a).all() and (host(db) == b).all()
+    hb.PolyMultiplyMulti(ntts, da, da, db)  # result aliases a
+    assert (host(da) == conv).all()
+    da = dev(a)
+    hb.PolyMultiplyMulti(ntts, db, da, db)  # result aliases b
+    assert (host(db) == conv).all() and (host(da) == a).all()
+    hb.PolyMultiplyMulti(ntts, h, a, b, group)  # host pointers
+    assert (h == conv).all()
+
+
 def test_multi_modulus_more_than_one_parameter_block(hb, checker):
     n, group = 256, 2
     mods = hb.GeneratePrimes(70, 40, True, n)

@@ -125,6 +125,26 @@ def main():
     units = L * pb
     print(f"* {units} residue products (batch {pb} x {L} moduli) in {t * 1e3:.2f} ms = **{units / t / 1e3:.1f} k products/s**, "
           f"{72.0 * n * units / t / 1e9:.0f} GB/s algorithmic (72N B per product, unfused)")
+    # the same work as ONE call: hexl_b200_poly_multiply_multi (multi-modulus launches, lazy transforms)
+    Aall, Ball = torch.cat([x.reshape(-1) for x in A]), torch.cat([x.reshape(-1) for x in B])
+    out = torch.empty_like(Aall)
+    tm = gpu_time(lambda: hb.PolyMultiplyMulti(ntts, out, Aall, Ball, pb), reps=3)
+    print(f"* as one `hexl_b200_poly_multiply_multi` call (6 launches): {tm * 1e3:.2f} ms = **{units / tm / 1e3:.1f} k products/s**")
+    del Aall, Ball, out
+    for pb_small in (1, 2):
+        As = torch.cat([x[:pb_small].reshape(-1) for x in A]); Bs = torch.cat([x[:pb_small].reshape(-1) for x in B])
+        outs = torch.empty_like(As)
+        t1 = gpu_time(lambda: hb.PolyMultiplyMulti(ntts, outs, As, Bs, pb_small), reps=20)
+
+        def per_call():
+            for i, q in enumerate(mods):
+                sl = slice(i * pb_small * n, (i + 1) * pb_small * n)
+                ntts[i].ComputeForward(As[sl], As[sl], 1, 4)
+                ntts[i].ComputeForward(Bs[sl], Bs[sl], 1, 4)
+                hb.EltwiseMultMod(As[sl], As[sl], Bs[sl], pb_small * n, q, 4)
+                ntts[i].ComputeInverse(As[sl], As[sl], 1, 1)
+        t2 = gpu_time(per_call, reps=20)
+        print(f"* {pb_small} polynomial(s) x {L} moduli (one ciphertext component): one call {t1 * 1e6:.0f} us vs {4 * L} per-modulus calls {t2 * 1e6:.0f} us ({t2 / t1:.1f}x)")
     hxa = np.random.default_rng(1).integers(0, mods[0], size=n * 32, dtype=np.uint64)
     hxb = np.random.default_rng(2).integers(0, mods[0], size=n * 32, dtype=np.uint64)
     if ref.kind == "reference":
