@@ -95,6 +95,8 @@ _sig("hexl_b200_ntt_inverse", _int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_ntt_forward_multi", _int, [C.POINTER(_vp), _u64, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_ntt_inverse_multi", _int, [C.POINTER(_vp), _u64, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_eltwise_mult_mod_multi", _int, [_vp, _vp, _vp, _u64, _vp, _u64, _u64, _vp])
+_sig("hexl_b200_eltwise_add_mod_multi", _int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp])
+_sig("hexl_b200_eltwise_sub_mod_multi", _int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp])
 _sig("hexl_b200_poly_multiply_multi", _int, [C.POINTER(_vp), _u64, _vp, _vp, _vp, _u64, _vp])
 _sig("hexl_b200_eltwise_add_mod", _int, [_vp, _vp, _vp, _u64, _u64, _vp])
 _sig("hexl_b200_eltwise_add_mod_scalar", _int, [_vp, _vp, _u64, _u64, _u64, _vp])
@@ -302,6 +304,21 @@ def EltwiseMultModMulti(result, operand1, operand2, n_per_modulus, moduli, input
     _check(_lib.hexl_b200_eltwise_mult_mod_multi(rp, ap, bp, n_per_modulus, mods.ctypes.data, mods.size,
                                                  input_mod_factor, _stream(stream, rc or ac)))
     return result
+
+
+def _addsub_multi(fn, result, operand1, operand2, n_per_modulus, moduli, stream):
+    mods = np.ascontiguousarray(moduli, dtype=np.uint64)
+    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1); bp, _, _ = _buf(operand2)
+    _check(fn(rp, ap, bp, n_per_modulus, mods.ctypes.data, mods.size, _stream(stream, rc or ac)))
+    return result
+
+
+def EltwiseAddModMulti(result, operand1, operand2, n_per_modulus, moduli, stream=None):
+    return _addsub_multi(_lib.hexl_b200_eltwise_add_mod_multi, result, operand1, operand2, n_per_modulus, moduli, stream)
+
+
+def EltwiseSubModMulti(result, operand1, operand2, n_per_modulus, moduli, stream=None):
+    return _addsub_multi(_lib.hexl_b200_eltwise_sub_mod_multi, result, operand1, operand2, n_per_modulus, moduli, stream)
 
 
 def PolyMultiplyMulti(ntts, result, a, b, batch_per_modulus=None, stream=None):

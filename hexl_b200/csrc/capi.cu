@@ -1055,23 +1055,22 @@ int hexl_b200_ntt_get_cached(hexl_b200_ntt** out, uint64_t degree, uint64_t q) {
 }
 
 // device side of EltwiseMultMod over an RNS batch
-static int rns_mult_on_device(uint64_t* result, const uint64_t* a, const uint64_t* b, uint64_t per_mod,
-                              const uint64_t* moduli, uint64_t num_moduli, int in_mf, cudaStream_t s) {
+static int rns_eltwise_on_device(int op, uint64_t* result, const uint64_t* a, const uint64_t* b, uint64_t per_mod,
+                                 const uint64_t* moduli, uint64_t num_moduli, int in_mf, cudaStream_t s) {
   for (uint64_t first = 0; first < num_moduli; first += kParamBlock) {
     const uint64_t count = std::min<uint64_t>(kParamBlock, num_moduli - first);
     DyadicModuli mods;
     for (uint64_t i = 0; i < count; ++i) mods.m[i] = dyadic_modulus(moduli[first + i]);
     const uint64_t off = first * per_mod;
-    cudaError_t e = launch_rns_mult(result + off, a + off, b + off, per_mod, count, in_mf, mods, s);
-    if (e != cudaSuccess) return cuda_fail(e, "EltwiseMultMod (RNS batch) launch");
+    cudaError_t e = launch_rns_eltwise(op, result + off, a + off, b + off, per_mod, count, in_mf, mods, s);
+    if (e != cudaSuccess) return cuda_fail(e, "eltwise (RNS batch) launch");
   }
   return 0;
 }
 
-int hexl_b200_eltwise_mult_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
-                                     uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli,
-                                     uint64_t in_mf, void* stream) {
-  // eltwise-mult-mod.cpp:23-36, per modulus
+static int rns_eltwise_entry(int op, uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                             uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli, uint64_t in_mf,
+                             void* stream) {
   REQUIRE(result && operand1 && operand2 && moduli, "Require result, operand1, operand2, moduli != nullptr");
   REQUIRE(n_per_modulus != 0 && num_moduli != 0, "Require n != 0");
   REQUIRE(in_mf == 1 || in_mf == 2 || in_mf == 4, "Require input_mod_factor = 1, 2, or 4");
@@ -1088,8 +1087,8 @@ int hexl_b200_eltwise_mult_mod_multi(uint64_t* result, const uint64_t* operand1,
       if (int rc = check_bounds(operand1 + i * n_per_modulus, n_per_modulus, moduli[i] * in_mf, pi, "operand1")) return rc;
       if (int rc = check_bounds(operand2 + i * n_per_modulus, n_per_modulus, moduli[i] * in_mf, pi, "operand2")) return rc;
     }
-    if (int rc = rns_mult_on_device(result, operand1, operand2, n_per_modulus, moduli, num_moduli, (int)in_mf,
-                                    (cudaStream_t)stream))
+    if (int rc = rns_eltwise_on_device(op, result, operand1, operand2, n_per_modulus, moduli, num_moduli, (int)in_mf,
+                                       (cudaStream_t)stream))
       return rc;
     return finish_device_call(pi, stream);
   }
@@ -1099,9 +1098,23 @@ int hexl_b200_eltwise_mult_mod_multi(uint64_t* result, const uint64_t* operand1,
   if (int rc = ws.get(&d2, total)) return rc;
   CU(cudaMemcpyAsync(d1, operand1, total * 8, cudaMemcpyHostToDevice, nullptr));
   CU(cudaMemcpyAsync(d2, operand2, total * 8, cudaMemcpyHostToDevice, nullptr));
-  if (int rc = rns_mult_on_device(d1, d1, d2, n_per_modulus, moduli, num_moduli, (int)in_mf, nullptr)) return rc;
+  if (int rc = rns_eltwise_on_device(op, d1, d1, d2, n_per_modulus, moduli, num_moduli, (int)in_mf, nullptr)) return rc;
   CU(cudaMemcpy(result, d1, total * 8, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+int hexl_b200_eltwise_mult_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                                     uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli,
+                                     uint64_t in_mf, void* stream) {
+  return rns_eltwise_entry(kRnsMult, result, operand1, operand2, n_per_modulus, moduli, num_moduli, in_mf, stream);
+}
+int hexl_b200_eltwise_add_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                                    uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli, void* stream) {
+  return rns_eltwise_entry(kRnsAdd, result, operand1, operand2, n_per_modulus, moduli, num_moduli, 1, stream);
+}
+int hexl_b200_eltwise_sub_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                                    uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli, void* stream) {
+  return rns_eltwise_entry(kRnsSub, result, operand1, operand2, n_per_modulus, moduli, num_moduli, 1, stream);
 }
 
 // FwdNTT(a), FwdNTT(b) (lazy outputs), point-wise product, InvNTT: all moduli per launch
@@ -1116,7 +1129,7 @@ static int poly_multiply_on_device(int dev, hexl_b200_ntt* const* handles, uint6
   for (uint64_t i = 0; i < count; ++i) moduli[i] = handles[i]->q;
   if (int rc = ntt_multi_on_device(true, dev, handles, count, result, a, 4, group, s)) return rc;
   if (int rc = ntt_multi_on_device(true, dev, handles, count, fb, b, 4, group, s)) return rc;
-  if (int rc = rns_mult_on_device(result, result, fb, group * n, moduli.data(), count, 4, s)) return rc;
+  if (int rc = rns_eltwise_on_device(kRnsMult, result, result, fb, group * n, moduli.data(), count, 4, s)) return rc;
   return ntt_multi_on_device(false, dev, handles, count, result, result, 1, group, s);
 }
 

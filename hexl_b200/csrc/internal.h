@@ -96,9 +96,10 @@ struct KeyPointers {
 // moduli [first, first + count) of a DyadicMultiply over `num_moduli` moduli
 cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, u64 n, u64 num_moduli, u64 first,
                                    u64 count, const DyadicModuli& mods, cudaStream_t stream);
-// EltwiseMultMod of `count` blocks of per_mod elements, block e under mods.m[e]; inputs < in_mf * q
-cudaError_t launch_rns_mult(u64* result, const u64* a, const u64* b, u64 per_mod, u64 count, int in_mf,
-                            const DyadicModuli& mods, cudaStream_t stream);
+// EltwiseMultMod / AddMod / SubMod of `count` blocks of per_mod elements, block e under mods.m[e]
+enum : int { kRnsMult = 0, kRnsAdd = 1, kRnsSub = 2 };
+cudaError_t launch_rns_eltwise(int op, u64* result, const u64* a, const u64* b, u64 per_mod, u64 count, int in_mf,
+                               const DyadicModuli& mods, cudaStream_t stream);
 
 // KeySwitch glue, batched over the RNS moduli of one parameter block (entry e of `mods`
 // describes modulus i0 + e).  KsModulus.a/b/c mean, per kernel:

@@ -79,12 +79,13 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
-// ---- EltwiseMultMod over an RNS batch: block e of per_mod elements under modulus e
-// (eltwise-mult-mod-internal.hpp:33-101 per element; inputs < in_mf * q_e, in_mf in {1,2,4}).
+// ---- EltwiseMultMod / AddMod / SubMod over an RNS batch: block e of per_mod elements under
+// modulus e (eltwise-mult-mod-internal.hpp:33-101, eltwise-add-mod.cpp:16-40, eltwise-sub-mod.cpp:16-40
+// per element; MultMod inputs < in_mf * q_e with in_mf in {1,2,4}, Add/Sub inputs < q_e).
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
-    rns_mult_kernel(u64* result, const u64* a, const u64* b, u64 per_mod, u64 count, int in_mf,
-                    const __grid_constant__ DyadicModuli mods) {
+    rns_eltwise_kernel(u64* result, const u64* a, const u64* b, u64 per_mod, u64 count, int op, int in_mf,
+                       const __grid_constant__ DyadicModuli mods) {
   const u64 total = per_mod * count / VEC;
   const u64 stride = (u64)gridDim.x * kThreads;
   for (u64 i = (u64)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
@@ -95,6 +96,14 @@ __global__ void __launch_bounds__(kThreads)
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       u64 xv = x.v[k], yv = y.v[k];
+      if (op == kRnsAdd) {
+        r.v[k] = csub(xv + yv, c.q);
+        continue;
+      }
+      if (op == kRnsSub) {
+        r.v[k] = xv >= yv ? xv - yv : xv + c.q - yv;
+        continue;
+      }
       if (in_mf >= 4) {
         xv = csub(xv, c.q << 1);
         yv = csub(yv, c.q << 1);
@@ -210,8 +219,8 @@ cudaError_t launch_dyadic_multiply(u64* result, const u64* op1, const u64* op2, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_rns_mult(u64* result, const u64* a, const u64* b, u64 per_mod, u64 count, int in_mf,
-                            const DyadicModuli& mods, cudaStream_t stream) {
+cudaError_t launch_rns_eltwise(int op, u64* result, const u64* a, const u64* b, u64 per_mod, u64 count, int in_mf,
+                               const DyadicModuli& mods, cudaStream_t stream) {
   const u64 total = per_mod * count;
   if (total == 0) return cudaSuccess;
   int dev = 0, sms = 148;
@@ -222,9 +231,9 @@ cudaError_t launch_rns_mult(u64* result, const u64* a, const u64* b, u64 per_mod
   u64 blocks = blocks_for(vec ? total / 2 : total);
   if (blocks > (u64)sms * 16) blocks = (u64)sms * 16;
   if (vec)
-    rns_mult_kernel<2><<<(unsigned)blocks, kThreads, 0, stream>>>(result, a, b, per_mod, count, in_mf, mods);
+    rns_eltwise_kernel<2><<<(unsigned)blocks, kThreads, 0, stream>>>(result, a, b, per_mod, count, op, in_mf, mods);
   else
-    rns_mult_kernel<1><<<(unsigned)blocks, kThreads, 0, stream>>>(result, a, b, per_mod, count, in_mf, mods);
+    rns_eltwise_kernel<1><<<(unsigned)blocks, kThreads, 0, stream>>>(result, a, b, per_mod, count, op, in_mf, mods);
   count_launch();
   return cudaGetLastError();
 }

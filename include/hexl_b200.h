@@ -151,6 +151,11 @@ int hexl_b200_ntt_inverse_multi(hexl_b200_ntt* const* handles, uint64_t count, u
 int hexl_b200_eltwise_mult_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
                                      uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli,
                                      uint64_t input_mod_factor, void* stream);
+/* EltwiseAddMod / EltwiseSubMod (eltwise-add-mod.hpp:22, eltwise-sub-mod.hpp:22) over an RNS batch */
+int hexl_b200_eltwise_add_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                                    uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli, void* stream);
+int hexl_b200_eltwise_sub_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
+                                    uint64_t n_per_modulus, const uint64_t* moduli, uint64_t num_moduli, void* stream);
 int hexl_b200_poly_multiply_multi(hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
                                   const uint64_t* a, const uint64_t* b, uint64_t batch_per_modulus, void* stream);
 

@@ -258,6 +258,10 @@ def test_rns_product_pipeline_matches_oracle(hb, checker, logn, group, nmods):
     h = np.zeros_like(a)
     hb.EltwiseMultModMulti(h, a, b, sz, mods)
     assert (h == prod).all()
+    for fn, ref in ((hb.EltwiseAddModMulti, checker.add_mod), (hb.EltwiseSubModMulti, checker.sub_mod)):
+        exp = np.concatenate([ref(a[i * sz:(i + 1) * sz], b[i * sz:(i + 1) * sz], q) for i, q in enumerate(mods)])
+        fn(o, dev(a), dev(b), sz, mods)
+        assert (host(o) == exp).all()
     conv = np.concatenate([
         checker.ntt_inverse(checker.mult_mod(checker.ntt_forward(a[i * sz:(i + 1) * sz], n, q),
                                              checker.ntt_forward(b[i * sz:(i + 1) * sz], n, q), q), n, q)
