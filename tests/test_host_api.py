@@ -141,6 +141,33 @@ def test_argument_validation_mirrors_hexl_checks(hb):
         assert ei.value.code == -1
 
 
+def test_argument_validation_of_the_batched_and_composite_entry_points(hb):
+    """cheap checks of the RNS-batched calls and the SEAL composites fire before any device work"""
+    E = hb.HexlB200Error
+    a8, b8, c16 = hb.NTT(8, 769), hb.NTT(8, 17), hb.NTT(16, 769)
+    x = np.arange(16, dtype=np.uint64)
+    y = np.zeros(16, dtype=np.uint64)
+    big = hb.NTT(8, hb.GeneratePrimes(1, 61, True, 8)[0])  # >= 2^61: lazy products would overflow
+    bad = [
+        lambda: hb.ComputeForwardMulti([a8, c16], y, x, 1, 1, 1),          # mixed degrees
+        lambda: hb.ComputeForwardMulti([a8, b8], y, x, 3, 1, 1),           # bad input factor
+        lambda: hb.ComputeInverseMulti([a8, b8], y, x, 1, 4, 1),           # bad output factor
+        lambda: hb.EltwiseMultModMulti(y, x, x, 8, [769, 17], 3),          # bad input factor
+        lambda: hb.EltwiseMultModMulti(y, x, x, 8, [769, 1], 1),           # modulus <= 1
+        lambda: hb.EltwiseAddModMulti(y, x, x, 0, [769, 17]),              # n == 0
+        lambda: hb.PolyMultiplyMulti([a8, c16], y, x, x, 1),               # mixed degrees
+        lambda: hb.PolyMultiplyMulti([a8, big], y, x, x, 1),               # modulus too large for the lazy pipeline
+        lambda: hb.DyadicMultiply(y, x, x, 0, [769]),                      # n == 0
+        lambda: hb.DyadicMultiply(np.zeros(24, dtype=np.uint64), x, x, 8, [1 << 62]),
+        lambda: hb.KeySwitch(y, x, 8, 1, 1, 2, 2, [769, 17], [x], [1]),    # key_modulus_size < rns_modulus_size
+        lambda: hb.KeySwitch(y, x, 6, 1, 2, 2, 2, [769, 17], [x], [1]),    # n not a power of two
+    ]
+    for i, f in enumerate(bad):
+        with pytest.raises(E) as ei:
+            f()
+        assert ei.value.code == -1, i
+
+
 def test_no_cpu_fallback_without_gpu(hb):
     """The product path must fail loudly when no CUDA device is usable."""
     if hb.device_count() > 0:
@@ -150,7 +177,12 @@ def test_no_cpu_fallback_without_gpu(hb):
     y = np.zeros_like(x)
     for f in (lambda: t.ComputeForward(y, x, 1, 1), lambda: t.ComputeInverse(y, x, 1, 1),
               lambda: hb.EltwiseAddMod(y, x, x, 8, 769), lambda: hb.EltwiseMultMod(y, x, x, 8, 769, 1),
-              lambda: hb.EltwiseReduceMod(y, x, 8, 769, 769, 1)):
+              lambda: hb.EltwiseReduceMod(y, x, 8, 769, 769, 1),
+              lambda: hb.ComputeForwardMulti([t, hb.NTT(8, 17)], np.zeros(16, dtype=np.uint64), np.arange(16, dtype=np.uint64) % 17),
+              lambda: hb.PolyMultiplyMulti([t], y, x, x, 1),
+              lambda: hb.EltwiseMultModMulti(y, x, x, 8, [769]),
+              lambda: hb.DyadicMultiply(np.zeros(12, dtype=np.uint64), np.arange(8, dtype=np.uint64) % 5,
+                                        np.arange(8, dtype=np.uint64) % 5, 4, [769])):
         with pytest.raises(hb.HexlB200Error) as ei:
             f()
         assert ei.value.code == -2  # HEXL_B200_ERR_NO_DEVICE
