@@ -396,6 +396,17 @@ def run_b200_arm(args):
         v, kind, tier = cpu_leg(n, q, threads, polys, 3)
         cpu = {"value": v, "unit": "NTT/s", "cores": threads, "kind": kind,
                "sample": f"{polys} polynomials x (forward + inverse), best of 3, {threads} threads, tier {tier}"}
+        # the checker also looks at what the timed kernels produced: the first and last 4 polynomials of
+        # the device-resident forward output y and round trip z, bit for bit (outside every timed region)
+        import oracle
+        chk = oracle.best_checker()
+        idx = list(range(4)) + list(range(batch - 4, batch))
+        hx = np.stack([x[i].cpu().numpy().view(np.uint64) for i in idx])
+        hy = np.stack([y[i].cpu().numpy().view(np.uint64) for i in idx])
+        hz = np.stack([z[i].cpu().numpy().view(np.uint64) for i in idx])
+        ok = bool((hy.reshape(-1) == chk.ntt_forward(hx.reshape(-1), n, q, 1, 1)).all() and (hz == hx).all())
+        cpu["parity"] = {"polynomials_checked": len(idx), "bit_exact": ok, "checker": chk.kind}
+        assert ok, "device results differ from the checker"
 
     if rank == 0:
         line = {
