@@ -874,9 +874,13 @@ __global__ void __launch_bounds__(DsmemCfg<LOGR>::THREADS, DsmemCfg<LOGR>::MIN_B
   __shared__ Twiddle32 stw[Cfg::R];
   const unsigned rank = blockIdx.x % Cfg::K;
   const u64 poly_off = (u64)(blockIdx.x / Cfg::K) << (Cfg::LOGC + LOGR);
+  // a CTA's shared memory may only be written by its peers once it is known to be running:
+  // arrive now, wait just before the first remote store
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
     if (l) stw[l] = ld_tw(tw + l);
   __syncthreads();
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
   // phase 1: my columns of every row -> the row owners' shared memory
   unsigned owner_base[Cfg::K];
 #pragma unroll
