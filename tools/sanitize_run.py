@@ -14,7 +14,8 @@ import hexl_b200 as hb  # noqa: E402
 
 g = torch.Generator(device="cuda").manual_seed(0)
 for logn, bits, batch in ((3, 20, 3), (6, 29, 5), (10, 29, 5), (10, 55, 5), (11, 60, 3), (12, 55, 2), (12, 29, 2),
-                          (13, 50, 1), (14, 29, 1), (14, 61, 1), (16, 55, 1), (16, 29, 1)):
+                          (13, 50, 1), (14, 29, 1), (14, 61, 1), (15, 29, 1), (16, 55, 1), (16, 29, 1), (17, 29, 1),
+                          (17, 50, 1)):
     n = 1 << logn
     q = hb.GeneratePrimes(1, bits, True, n)[0]
     t = hb.NTT(n, q)
