@@ -89,3 +89,18 @@ def test_swizzle_is_a_bijection_inside_aligned_blocks(elem_bytes):
     s = swz(j, elem_bytes)
     blk = 16 if elem_bytes == 8 else 32
     assert (np.sort(s) == j).all() and ((s // blk) == (j // blk)).all()
+
+
+@pytest.mark.parametrize("logr", [2, 3, 4, 5])
+def test_cluster_row_ownership_is_consistent(logr):
+    """ntt_dsmem_fwd/inv: the column phase stores row e into CTA e % K, slot e // K; the row
+    phase of CTA `rank` transforms rows rank + lr*K from slot lr.  Both views must describe the
+    same bijection between the R rows and the K x (R/K) shared-memory slots."""
+    r = 1 << logr
+    k = min(r, 8)
+    rpc = r // k
+    scatter = {(e % k, e // k): e for e in range(r)}
+    assert len(scatter) == r and set(scatter) == {(c, s) for c in range(k) for s in range(rpc)}
+    for rank in range(k):
+        for lr in range(rpc):
+            assert scatter[(rank, lr)] == rank + lr * k
