@@ -90,6 +90,7 @@ _sig("hexl_b200_ntt_degree", _u64, [_vp])
 _sig("hexl_b200_ntt_modulus", _u64, [_vp])
 _sig("hexl_b200_ntt_minimal_root", _u64, [_vp])
 _sig("hexl_b200_ntt_table", C.POINTER(_u64), [_vp, _int])
+_sig("hexl_b200_ntt_prepare", _int, [_vp, _int])
 _sig("hexl_b200_ntt_forward", _int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_ntt_inverse", _int, [_vp, _vp, _vp, _u64, _u64, _u64, _vp])
 _sig("hexl_b200_ntt_forward_multi", _int, [C.POINTER(_vp), _u64, _vp, _vp, _u64, _u64, _u64, _vp])
@@ -137,6 +138,11 @@ def _buf(x):
     assert isinstance(x, np.ndarray) and x.dtype == np.uint64 and x.flags["C_CONTIGUOUS"], \
         "host buffers must be C-contiguous numpy uint64 arrays"
     return x.ctypes.data, x.size, False
+
+
+def _need(what: str, have: int, want: int) -> None:
+    if have < want:
+        raise HexlB200Error(-1, f"{what}: buffer holds {have} elements, the call needs {want}")
 
 
 def _stream(stream, any_cuda: bool):
@@ -240,6 +246,11 @@ class NTT:
     def CheckArguments(degree, modulus) -> bool:
         return bool(_lib.hexl_b200_ntt_check_arguments(degree, modulus))
 
+    def Prepare(self, device: int = -1):
+        """upload the tables to `device` now (needed before capturing a cold handle into a CUDA graph)"""
+        _check(_lib.hexl_b200_ntt_prepare(self._h, device))
+        return self
+
     def GetDegree(self): return int(_lib.hexl_b200_ntt_degree(self._h))
     def GetModulus(self): return int(_lib.hexl_b200_ntt_modulus(self._h))
     def GetMinimalRootOfUnity(self): return int(_lib.hexl_b200_ntt_minimal_root(self._h))
@@ -300,7 +311,9 @@ def ComputeInverseMulti(ntts, result, operand, input_mod_factor=1, output_mod_fa
 def EltwiseMultModMulti(result, operand1, operand2, n_per_modulus, moduli, input_mod_factor=1, stream=None):
     """EltwiseMultMod over an RNS batch in one launch: block e (n_per_modulus elements) under moduli[e]"""
     mods = np.ascontiguousarray(moduli, dtype=np.uint64)
-    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1); bp, _, _ = _buf(operand2)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(operand1); bp, bn, _ = _buf(operand2)
+    for what, have in (("result", rn), ("operand1", an), ("operand2", bn)):
+        _need(what, have, n_per_modulus * mods.size)
     _check(_lib.hexl_b200_eltwise_mult_mod_multi(rp, ap, bp, n_per_modulus, mods.ctypes.data, mods.size,
                                                  input_mod_factor, _stream(stream, rc or ac)))
     return result
@@ -308,7 +321,9 @@ def EltwiseMultModMulti(result, operand1, operand2, n_per_modulus, moduli, input
 
 def _addsub_multi(fn, result, operand1, operand2, n_per_modulus, moduli, stream):
     mods = np.ascontiguousarray(moduli, dtype=np.uint64)
-    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1); bp, _, _ = _buf(operand2)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(operand1); bp, bn, _ = _buf(operand2)
+    for what, have in (("result", rn), ("operand1", an), ("operand2", bn)):
+        _need(what, have, n_per_modulus * mods.size)
     _check(fn(rp, ap, bp, n_per_modulus, mods.ctypes.data, mods.size, _stream(stream, rc or ac)))
     return result
 
@@ -323,10 +338,12 @@ def EltwiseSubModMulti(result, operand1, operand2, n_per_modulus, moduli, stream
 
 def PolyMultiplyMulti(ntts, result, a, b, batch_per_modulus=None, stream=None):
     """Negacyclic products InvNTT(FwdNTT(a) .* FwdNTT(b)), polynomial u under ntts[u // batch_per_modulus]"""
-    rp, rn, rc = _buf(result); ap, an, ac = _buf(a); bp, _, _ = _buf(b)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(a); bp, bn, _ = _buf(b)
     n = ntts[0].GetDegree()
     if batch_per_modulus is None:
         batch_per_modulus = an // (n * len(ntts))
+    for what, have in (("result", rn), ("a", an), ("b", bn)):
+        _need(what, have, batch_per_modulus * n * len(ntts))
     hs = (_vp * len(ntts))(*[t._h for t in ntts])
     _check(_lib.hexl_b200_poly_multiply_multi(hs, len(ntts), rp, ap, bp, batch_per_modulus, _stream(stream, rc or ac)))
     return result
@@ -338,7 +355,10 @@ def _scalar(x) -> bool:
 
 
 def EltwiseAddMod(result, operand1, operand2, n, modulus, stream=None):
-    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(operand1)
+    _need("result", rn, n); _need("operand1", an, n)
+    if not _scalar(operand2):
+        _need("operand2", _buf(operand2)[1], n)
     if _scalar(operand2):
         _check(_lib.hexl_b200_eltwise_add_mod_scalar(rp, ap, int(operand2), n, modulus, _stream(stream, rc or ac)))
     else:
@@ -348,7 +368,10 @@ def EltwiseAddMod(result, operand1, operand2, n, modulus, stream=None):
 
 
 def EltwiseSubMod(result, operand1, operand2, n, modulus, stream=None):
-    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(operand1)
+    _need("result", rn, n); _need("operand1", an, n)
+    if not _scalar(operand2):
+        _need("operand2", _buf(operand2)[1], n)
     if _scalar(operand2):
         _check(_lib.hexl_b200_eltwise_sub_mod_scalar(rp, ap, int(operand2), n, modulus, _stream(stream, rc or ac)))
     else:
@@ -358,33 +381,40 @@ def EltwiseSubMod(result, operand1, operand2, n, modulus, stream=None):
 
 
 def EltwiseMultMod(result, operand1, operand2, n, modulus, input_mod_factor=1, stream=None):
-    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1); bp, _, _ = _buf(operand2)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(operand1); bp, bn, _ = _buf(operand2)
+    _need("result", rn, n); _need("operand1", an, n); _need("operand2", bn, n)
     _check(_lib.hexl_b200_eltwise_mult_mod(rp, ap, bp, n, modulus, input_mod_factor, _stream(stream, rc or ac)))
     return result
 
 
 def EltwiseFMAMod(result, arg1, arg2, arg3, n, modulus, input_mod_factor=1, stream=None):
-    rp, _, rc = _buf(result); ap, _, ac = _buf(arg1); cp, _, _ = _buf(arg3)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(arg1); cp, cn, _ = _buf(arg3)
+    _need("result", rn, n); _need("arg1", an, n)
+    if arg3 is not None:
+        _need("arg3", cn, n)
     _check(_lib.hexl_b200_eltwise_fma_mod(rp, ap, int(arg2), cp, n, modulus, input_mod_factor,
                                           _stream(stream, rc or ac)))
     return result
 
 
 def EltwiseReduceMod(result, operand, n, modulus, input_mod_factor, output_mod_factor, stream=None):
-    rp, _, rc = _buf(result); ap, _, ac = _buf(operand)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(operand)
+    _need("result", rn, n); _need("operand", an, n)
     _check(_lib.hexl_b200_eltwise_reduce_mod(rp, ap, n, modulus, input_mod_factor, output_mod_factor,
                                              _stream(stream, rc or ac)))
     return result
 
 
 def EltwiseCmpAdd(result, operand1, n, cmp, bound, diff, stream=None):
-    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(operand1)
+    _need("result", rn, n); _need("operand1", an, n)
     _check(_lib.hexl_b200_eltwise_cmp_add(rp, ap, n, int(cmp), bound, diff, _stream(stream, rc or ac)))
     return result
 
 
 def EltwiseCmpSubMod(result, operand1, n, modulus, cmp, bound, diff, stream=None):
-    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1)
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(operand1)
+    _need("result", rn, n); _need("operand1", an, n)
     _check(_lib.hexl_b200_eltwise_cmp_sub_mod(rp, ap, n, modulus, int(cmp), bound, diff,
                                               _stream(stream, rc or ac)))
     return result
@@ -403,8 +433,11 @@ def GetNTT(N: int, modulus: int) -> NTT:
 def DyadicMultiply(result, operand1, operand2, n, moduli, num_moduli=None, stream=None):
     """hexl/include/hexl/experimental/seal/dyadic-multiply.hpp:26"""
     mods = np.ascontiguousarray(moduli, dtype=np.uint64)
-    rp, _, rc = _buf(result); ap, _, ac = _buf(operand1); bp, _, _ = _buf(operand2)
-    _check(_lib.hexl_b200_dyadic_multiply(rp, ap, bp, n, mods.ctypes.data, num_moduli or mods.size,
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(operand1); bp, bn, _ = _buf(operand2)
+    nm = num_moduli or mods.size
+    _need("moduli", mods.size, nm); _need("result", rn, 3 * n * nm)
+    _need("operand1", an, 2 * n * nm); _need("operand2", bn, 2 * n * nm)
+    _check(_lib.hexl_b200_dyadic_multiply(rp, ap, bp, n, mods.ctypes.data, nm,
                                           _stream(stream, rc or ac)))
     return result
 
@@ -414,7 +447,13 @@ def KeySwitch(result, t_target_iter_ptr, n, decomp_modulus_size, key_modulus_siz
     """hexl/include/hexl/experimental/seal/key-switch.hpp:34; k_switch_keys is a list of buffers"""
     mods = np.ascontiguousarray(moduli, dtype=np.uint64)
     ms = np.ascontiguousarray(modswitch_factors, dtype=np.uint64)
-    rp, _, rc = _buf(result); tp, _, tc = _buf(t_target_iter_ptr)
+    rp, rn, rc = _buf(result); tp, tn, tc = _buf(t_target_iter_ptr)
+    _need("moduli", mods.size, key_modulus_size); _need("modswitch_factors", ms.size, decomp_modulus_size)
+    _need("k_switch_keys", len(k_switch_keys), decomp_modulus_size)
+    _need("result", rn, key_component_count * decomp_modulus_size * n)
+    _need("t_target_iter_ptr", tn, decomp_modulus_size * n)
+    for k in k_switch_keys[:decomp_modulus_size]:
+        _need("k_switch_keys[j]", _buf(k)[1], key_component_count * key_modulus_size * n)
     key_ptrs = (_vp * len(k_switch_keys))(*[_buf(k)[0] for k in k_switch_keys])
     _check(_lib.hexl_b200_key_switch(rp, tp, n, decomp_modulus_size, key_modulus_size, rns_modulus_size,
                                      key_component_count, mods.ctypes.data, key_ptrs, ms.ctypes.data,

@@ -260,7 +260,10 @@ int run_host(u64* result, const u64* a, const u64* b, u64 total, u64 unit, MakeL
   for (u64 d = 0; d < ndev && !rc; ++d) {
     const u64 lo = units * d / ndev * unit, hi = units * (d + 1) / ndev * unit;
     auto launch = make(devs[d]);
-    if (!launch.ok) return launch.rc;
+    if (!launch.ok) {
+      rc = launch.rc;  // fall through: copies already enqueued on other devices still target `result`
+      break;
+    }
     rc = run_host_on_device(devs[d], result + lo, a + lo, b ? b + lo : nullptr, hi - lo, unit, launch, false);
   }
   for (u64 d = 0; d < ndev; ++d) {
@@ -355,30 +358,61 @@ void build_tables(hexl_b200_ntt* h) {
   h->inv_n_w = make_twiddle(nt::mul_mod(inv_n, h->inv_tree[1].w, q), q);
 }
 
-int device_tables(hexl_b200_ntt* h, int dev, NttDeviceTables* out) {
+// Uploads the tables of h to device `dev` (the current device) on first use.  The cold path allocates and
+// copies synchronously, so it must not run inside a stream capture: hexl_b200_ntt_prepare warms a handle
+// explicitly, and a cold handle met during a capture is reported instead of invalidating the capture.
+int device_tables(hexl_b200_ntt* h, int dev, NttDeviceTables* out, cudaStream_t user_stream = nullptr) {
   std::lock_guard<std::mutex> lk(h->mu);
   auto it = h->dev.find(dev);
   if (it == h->dev.end()) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    // (the legacy default stream cannot be captured, and querying it during someone else's capture would
+    // invalidate that capture)
+    if (user_stream && cudaStreamIsCapturing(user_stream, &cap) != cudaSuccess) cudaGetLastError();
+    if (cap != cudaStreamCaptureStatusNone)
+      return fail(HEXL_B200_ERR_INVALID_ARG,
+                  "NTT tables for this device are not uploaded yet and the stream is being captured: call "
+                  "hexl_b200_ntt_prepare (or run the call once) before capturing");
     hexl_b200_ntt::Dev d;
+    auto release = [&d]() {
+      cudaFree(d.fwd);
+      cudaFree(d.inv);
+      cudaFree(d.fwd32);
+      cudaFree(d.inv32);
+      cudaFree(d.params);
+    };
+#define CU_T(call)                                        \
+  do {                                                    \
+    cudaError_t e__ = (call);                             \
+    if (e__ != cudaSuccess) {                             \
+      release();                                          \
+      return cuda_fail(e__, #call);                       \
+    }                                                     \
+  } while (0)
     const size_t bytes = h->n * sizeof(Twiddle);
-    CU(cudaMalloc(&d.fwd, bytes));
-    CU(cudaMalloc(&d.inv, bytes));
-    CU(cudaMemcpy(d.fwd, h->fwd_tree.data(), bytes, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d.inv, h->inv_tree.data(), bytes, cudaMemcpyHostToDevice));
+    CU_T(cudaMalloc(&d.fwd, bytes));
+    CU_T(cudaMalloc(&d.inv, bytes));
+    CU_T(cudaMemcpy(d.fwd, h->fwd_tree.data(), bytes, cudaMemcpyHostToDevice));
+    CU_T(cudaMemcpy(d.inv, h->inv_tree.data(), bytes, cudaMemcpyHostToDevice));
     if (h->q < kSmallModulusLimit) {
       std::vector<Twiddle32> f32(h->n), i32(h->n);
       for (uint64_t k = 0; k < h->n; ++k) {
         f32[k] = make_twiddle32(h->fwd_tree[k].w, h->q);
         i32[k] = make_twiddle32(h->inv_tree[k].w, h->q);
       }
-      CU(cudaMalloc(&d.fwd32, h->n * sizeof(Twiddle32)));
-      CU(cudaMalloc(&d.inv32, h->n * sizeof(Twiddle32)));
-      CU(cudaMemcpy(d.fwd32, f32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
-      CU(cudaMemcpy(d.inv32, i32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
+      CU_T(cudaMalloc(&d.fwd32, h->n * sizeof(Twiddle32)));
+      CU_T(cudaMalloc(&d.inv32, h->n * sizeof(Twiddle32)));
+      CU_T(cudaMemcpy(d.fwd32, f32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
+      CU_T(cudaMemcpy(d.inv32, i32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
     }
     NttDeviceParams hp{d.fwd, d.inv, h->q, nt::multiply_factor(1, 64, h->q), h->inv_n, h->inv_n_w};
-    CU(cudaMalloc(&d.params, sizeof(NttDeviceParams)));
-    CU(cudaMemcpy(d.params, &hp, sizeof(NttDeviceParams), cudaMemcpyHostToDevice));
+    CU_T(cudaMalloc(&d.params, sizeof(NttDeviceParams)));
+    CU_T(cudaMemcpy(d.params, &hp, sizeof(NttDeviceParams), cudaMemcpyHostToDevice));
+    // A pageable-source cudaMemcpy may return once the data sits in the driver's staging buffer; the
+    // kernels that read these tables run on non-blocking streams, which are not ordered against the
+    // legacy default stream.  Wait for the DMA to land before anybody can launch on the tables.
+    CU_T(cudaDeviceSynchronize());
+#undef CU_T
     NttDeviceTables& t = d.view;  // everything a launch needs, computed once
     t.dparams = d.params;
     t.fwd = d.fwd;
@@ -458,7 +492,7 @@ int ntt_compute(bool forward, hexl_b200_ntt* h, uint64_t* result, const uint64_t
     DeviceGuard g;
     if (int rc = g.enter(pi.device)) return rc;
     NttDeviceTables t;
-    if (int rc = device_tables(h, pi.device, &t)) return rc;
+    if (int rc = device_tables(h, pi.device, &t, (cudaStream_t)stream)) return rc;
     cudaError_t e = forward ? launch_ntt_forward(t, result, operand, (int)in_mf, (int)out_mf, batch, (cudaStream_t)stream)
                             : launch_ntt_inverse(t, result, operand, (int)in_mf, (int)out_mf, batch, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "NTT launch");
@@ -618,10 +652,15 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
         if (p) hexl_b200_ntt_release(p);
     }
   } release{h};
-  for (uint64_t i = 0; i < key_modulus_size; ++i)
-    if (int rc = cached_ntt(&h[i], n, moduli[i])) return rc;
-  // RNS modulus i of the computation lives in slot ki(i) of the key / moduli arrays (:62-63)
+  // RNS modulus i of the computation lives in slot ki(i) of the key / moduli arrays (:62-63); the slots
+  // between decomp and the special prime are not touched by this key switch
   auto ki = [&](uint64_t i) { return i == decomp ? key_modulus_size - 1 : i; };
+  for (uint64_t i = 0; i < rns; ++i) {
+    // lazy sums of the glue kernels (v < 4q in the MAC, < 8q in the final step) need 8q < 2^64
+    if (moduli[ki(i)] >= (1ull << 61))
+      return fail(HEXL_B200_ERR_INVALID_ARG, "KeySwitch: Require moduli < 2^61 (slot %llu)", (unsigned long long)ki(i));
+    if (int rc = cached_ntt(&h[ki(i)], n, moduli[ki(i)])) return rc;
+  }
   // moduli handled per round of step 2: bounded by the parameter block and by ~256 MiB of scratch
   const uint64_t per_mod = decomp * n;
   uint64_t ichunk = std::max<uint64_t>(1, (256ull << 20) / (per_mod * 8));
@@ -667,7 +706,7 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
   uint64_t* t_last = prod + decomp * kcc * n;  // [k][n], contiguous
   {
     NttDeviceTables tl;
-    if (int rc = device_tables(h[key_modulus_size - 1], dev, &tl)) return rc;
+    if (int rc = device_tables(h[key_modulus_size - 1], dev, &tl, s)) return rc;
     LAUNCH(launch_ntt_inverse(tl, t_last, t_last, 2, 2, kcc, s));
   }
   for (uint64_t i0 = 0; i0 < decomp; i0 += kParamBlock) {
@@ -700,7 +739,7 @@ int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, ui
     uint64_t min_q = ~0ull, max_q = 0;
     for (uint64_t i = 0; i < cnt; ++i) {
       NttDeviceTables t;
-      if (int rc = device_tables(handles[first + i], dev, &t)) return rc;
+      if (int rc = device_tables(handles[first + i], dev, &t, s)) return rc;
       multi.p[i] = t.dparams;
       min_q = std::min(min_q, t.q);
       max_q = std::max(max_q, t.q);
@@ -879,6 +918,16 @@ const uint64_t* hexl_b200_ntt_table(const hexl_b200_ntt* h, int which) {
     case 3: return h->inv_seq_precon.data();
   }
   return nullptr;
+}
+
+int hexl_b200_ntt_prepare(hexl_b200_ntt* h, int device) {
+  if (!h) return fail(HEXL_B200_ERR_INVALID_ARG, "ntt handle == nullptr");
+  if (device < 0) CU(cudaGetDevice(&device));
+  if (device >= hexl_b200_device_count()) return fail(HEXL_B200_ERR_INVALID_ARG, "device ordinal out of range");
+  DeviceGuard g;
+  if (int rc = g.enter(device)) return rc;
+  NttDeviceTables t;
+  return device_tables(h, device, &t);
 }
 
 int hexl_b200_ntt_forward(hexl_b200_ntt* h, uint64_t* result, const uint64_t* operand, uint64_t in_mf,

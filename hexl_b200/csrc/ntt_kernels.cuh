@@ -95,6 +95,7 @@ constexpr int kFastBound = 8;  // FAST inverse: every value is < 8q at a pass bo
 struct Mod {
   u64 q, two_q, four_q, mu;  // mu = floor(2^64 / q)
   unsigned n0, n1;           // low / high word of 2^64 - q
+  u64 bias;                  // kQuotBias * q mod 2^64 (FP64-assisted quotient, see TwH)
 };
 
 __device__ __forceinline__ unsigned lo32(u64 x) { return (unsigned)x; }
@@ -179,6 +180,94 @@ __device__ __forceinline__ u64 mul_tw_exact(u64 x, const Twiddle w, const Mod& m
   return mad_chain(x, w.w, mulhi(x, w.wp), m);
 }
 
+// ---- FP64-assisted quotient estimate (FAST mode, HEXL_B200_FP64Q).
+// The FMA-heavy pipe (IMAD / IMAD.WIDE) bounds the butterflies while the FP64 pipe idles.  Of the three
+// 32x32 products of mulhi_approx, the two cross terms  cross = (x1*b0 + x0*b1) / 2^32  (b = w') only
+// need ~33 significant bits, which two fused multiply-adds in binary64 deliver:
+//   A0 = 2^52 + x0, A1 = 2^52 + x1      bit patterns {0x43300000 : word}, no arithmetic
+//   beta_i = b_i / 2^32 (exact),   K = 2^52 + 2 - 2^20 (b0 + b1) (exact integer, |K| < 2^53)
+//   u = RD(A0*beta1 + K)      = x0*b1/2^32 + 2^52 + 2 - 2^20 b0 - [0,1)         in (0, 2^52 + 2^32 + 2]
+//   R = RD(A1*beta0 + u)      = 2^52 + 2 + cross - [0,2)                         in [2^52, 2^52 + 2^33 + 2]
+// so bits(R) = kQuotBias + c with c an integer in (cross - 2, cross]: Q = x1*b1 + c is low by 0, 1 or 2
+// exactly like mulhi_approx (tools/fp64_quot_model.py checks this with exact rationals).  The constant
+// kQuotBias rides along in Q; kQuotBias*q is added back through the accumulator of the first product of
+// the multiply-add chain (Mod::bias), so it costs nothing.
+constexpr u64 kQuotBias = 0x4330000000000002ull;
+struct TwH {
+  u64 w;
+  double beta0, beta1, K;
+  unsigned b1;
+};
+__device__ __forceinline__ double fma_rd(double a, double b, double c) {
+  double r;
+  asm("fma.rm.f64 %0, %1, %2, %3;" : "=d"(r) : "d"(a), "d"(b), "d"(c));
+  return r;
+}
+#ifndef HEXL_B200_FP64Q
+#define HEXL_B200_FP64Q 0
+#endif
+// HEXL_B200_FP64Q: 1 = operand words and twiddle words enter binary64 as {constant : word} register pairs;
+// 2 = operand words through I2F.F64.U32 (conversion unit; K is then the constant 2^52 + 2), twiddle words as pairs;
+// 3 = I2F.F64.U32 on both sides.
+__device__ __forceinline__ TwH expand_tw(const Twiddle t) {
+  unsigned b0, b1;
+  split(t.wp, b0, b1);
+  TwH h;
+  h.w = t.w;
+  h.b1 = b1;
+#if HEXL_B200_FP64Q == 3
+  h.beta0 = __uint2double_rn(b0) * (1.0 / 4294967296.0);
+  h.beta1 = __uint2double_rn(b1) * (1.0 / 4294967296.0);
+#else
+  // {0x41300000 : b} is 2^20 + b/2^32
+  h.beta0 = __hiloint2double(0x41300000, (int)b0) - 1048576.0;
+  h.beta1 = __hiloint2double(0x41300000, (int)b1) - 1048576.0;
+#endif
+#if HEXL_B200_FP64Q == 1
+  h.K = fma(h.beta0 + h.beta1, -4503599627370496.0, 4503599627370498.0);
+#else
+  h.K = 4503599627370498.0;
+#endif
+  return h;
+}
+// x*w mod q in [0,4q) for x < 2^63
+__device__ __forceinline__ u64 mul_tw_h(u64 x, const TwH& w, const Mod& m) {
+  unsigned x0, x1, w0, w1, q0, q1, t0, t1;
+  split(x, x0, x1);
+#if HEXL_B200_FP64Q == 1
+  const double A0 = __hiloint2double(0x43300000, (int)x0), A1 = __hiloint2double(0x43300000, (int)x1);
+#else
+  const double A0 = __uint2double_rn(x0), A1 = __uint2double_rn(x1);
+#endif
+  const double R = fma_rd(A1, w.beta0, fma_rd(A0, w.beta1, w.K));
+  split(mad_wide(x1, w.b1, (u64)__double_as_longlong(R)), q0, q1);  // Q + kQuotBias
+  split(w.w, w0, w1);
+  split(mad_wide(q0, m.n0, mad_wide(x0, w0, m.bias)), t0, t1);
+  t1 = mad_lo(x0, w1, t1);
+  t1 = mad_lo(x1, w0, t1);
+  t1 = mad_lo(q0, m.n1, t1);
+  t1 = mad_lo(q1, m.n0, t1);
+  return join(t0, t1);
+}
+
+// the twiddle form a mode's butterflies consume
+template <int MODE>
+struct TwUse {
+  using T = typename Ar<MODE>::Tw;
+  static __device__ __forceinline__ T prep(const typename Ar<MODE>::Tw t) { return t; }
+};
+#if HEXL_B200_FP64Q
+template <>
+struct TwUse<kFast> {
+  using T = TwH;
+  static __device__ __forceinline__ TwH prep(const Twiddle t) { return expand_tw(t); }
+};
+template <int MODE>
+__device__ __forceinline__ u64 mul_tw(u64 x, const TwH& w, const Mod& m) {
+  return mul_tw_h(x, w, m);
+}
+#endif
+
 // any 64-bit value -> [0,2q):  x - floor(x*mu/2^64)*q, mu = floor(2^64/q)
 __device__ __forceinline__ u64 barrett_lazy(u64 x, const Mod& m) {
   unsigned q0, q1, t0, t1;
@@ -200,8 +289,8 @@ __device__ __forceinline__ u64 barrett_lazy_bigq(u64 x, const Mod& m) {
 }
 
 // ----------------------------------------------------------------- butterflies
-template <int MODE>
-__device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, const Twiddle w, const Mod& m) {
+template <int MODE, typename TW>
+__device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, const TW& w, const Mod& m) {
   if (MODE == kFast) {
     const u64 T = mul_tw<kFast>(Y, w, m);  // [0,4q)
     Y = X + m.four_q - T;
@@ -220,8 +309,8 @@ __device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, const Twiddle w, const 
 }
 
 // cq: a multiple of q at least as large as any Y of this stage (FAST only)
-template <int MODE>
-__device__ __forceinline__ void inv_bfly(u64& X, u64& Y, const Twiddle w, const Mod& m, u64 cq) {
+template <int MODE, typename TW>
+__device__ __forceinline__ void inv_bfly(u64& X, u64& Y, const TW& w, const Mod& m, u64 cq) {
   if (MODE == kFast) {
     const u64 d = X + cq - Y;
     X = X + Y;
@@ -271,16 +360,16 @@ __device__ __forceinline__ unsigned mul_tw32(unsigned x, const Twiddle32 w, cons
   const unsigned Q = hi32(mul_wide(x, w.wp));
   return mad_lo(Q, m.n0, x * w.w);  // n0 = low word of 2^64 - q = 2^32 - q
 }
-template <int MODE>
-__device__ __forceinline__ void fwd_bfly(unsigned& X, unsigned& Y, const Twiddle32 w, const Mod& m) {
+template <int MODE, typename TW>
+__device__ __forceinline__ void fwd_bfly(unsigned& X, unsigned& Y, const TW& w, const Mod& m) {
   const unsigned two_q = lo32(m.two_q);
   const unsigned tx = csub32(X, two_q);
   const unsigned T = mul_tw32(Y, w, m);
   X = tx + T;
   Y = tx + two_q - T;
 }
-template <int MODE>
-__device__ __forceinline__ void inv_bfly(unsigned& X, unsigned& Y, const Twiddle32 w, const Mod& m, unsigned) {
+template <int MODE, typename TW>
+__device__ __forceinline__ void inv_bfly(unsigned& X, unsigned& Y, const TW& w, const Mod& m, unsigned) {
   const unsigned two_q = lo32(m.two_q);
   const unsigned s = X + Y;
   const unsigned d = X + two_q - Y;
@@ -415,13 +504,14 @@ __device__ __forceinline__ void reg_stages(typename Ar<MODE>::E (&v)[16], unsign
       }
 #pragma unroll
       for (int g = 0; g < (8 >> eb); ++g) {
+        const typename TwUse<MODE>::T wg = TwUse<MODE>::prep(wc[g]);
 #pragma unroll
         for (int l = 0; l < (1 << eb); ++l) {
           const int e = (g << (eb + 1)) | l;
           if (FWD)
-            fwd_bfly<MODE>(v[e], v[e | (1 << eb)], wc[g], m);
+            fwd_bfly<MODE>(v[e], v[e | (1 << eb)], wg, m);
           else
-            inv_bfly<MODE>(v[e], v[e | (1 << eb)], wc[g], m, cq);
+            inv_bfly<MODE>(v[e], v[e | (1 << eb)], wg, m, cq);
         }
       }
     }
@@ -679,7 +769,7 @@ __device__ __forceinline__ void col_stages(typename Ar<MODE>::E (&v)[1 << LOGR],
     } else {
 #pragma unroll
       for (int gi = 0; gi < (1 << s); ++gi) {
-        const Tw w = stw[(1 << s) + gi];
+        const typename TwUse<MODE>::T w = TwUse<MODE>::prep(stw[(1 << s) + gi]);
 #pragma unroll
         for (int l = 0; l < (1 << eb); ++l) {
           const int e = (gi << (eb + 1)) | l;
@@ -1051,6 +1141,7 @@ __host__ __device__ inline Mod make_mod(u64 q, u64 mu) {
   const u64 negq = 0 - q;
   m.n0 = (unsigned)negq;
   m.n1 = (unsigned)(negq >> 32);
+  m.bias = kQuotBias * q;
   return m;
 }
 inline Mod make_mod(const NttDeviceTables& t) { return make_mod(t.q, t.mu); }

@@ -410,6 +410,8 @@ class NTT {
 
   // extension: the underlying C handle (e.g. to pass across an FFI)
   hexl_b200_ntt* Handle() const { return m_handle; }
+  // extension: upload the tables to `device` (-1 = current) now, e.g. before capturing calls into a CUDA graph
+  void Prepare(int device = -1) { b200_detail::Throw(hexl_b200_ntt_prepare(m_handle, device)); }
   // extension: the process-wide cached object for (N, modulus) -- GetNTT below
   static NTT FromCache(uint64_t degree, uint64_t q) {
     NTT t;

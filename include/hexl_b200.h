@@ -114,6 +114,13 @@ uint64_t hexl_b200_ntt_minimal_root(const hexl_b200_ntt* h);     /* GetMinimalRo
  * 3 their 64-bit Shoup factors.  Returns a pointer valid for the handle's life. */
 const uint64_t* hexl_b200_ntt_table(const hexl_b200_ntt* h, int which);
 
+/* Uploads the handle's tables to `device` (-1: the calling thread's current device) now instead of on
+ * the first transform there.  The first use of a handle on a device allocates and copies synchronously,
+ * which is not allowed while a stream is being captured into a CUDA graph: warm the handles (this call,
+ * or one ordinary call) before capturing.  No counterpart in the reference (its tables live in host
+ * memory, ntt-internal.cpp:54-169). */
+int hexl_b200_ntt_prepare(hexl_b200_ntt* h, int device);
+
 /* NTT::ComputeForward (ntt.hpp:99; ntt-internal.cpp:188-250): natural-order input,
  * bit-reversed output.  in_mf in {1,2,4}: inputs < in_mf*q; out_mf in {1,4}:
  * outputs in [0, out_mf*q).  `batch` polynomials back to back. */

@@ -1,0 +1,178 @@
+"""Parity at the exact shapes BASELINE.json's north_star names (configs[3] and configs[4]) and of
+the product's own multi-GPU mechanism (hexl_b200_set_host_devices), through the C ABI.
+
+    C4  FwdNTT -> EltwiseMultMod -> InvNTT, N = 2^17, 16 moduli = GeneratePrimes(16, 60, true, 2^17)
+    C5  CKKS KeySwitch, N = 2^15, 30 RNS moduli (decomp_modulus_size 29 + the special prime)
+        hexl/experimental/seal/key-switch-internal.cpp:25-201
+
+The checker is the compiled reference when oracle/_ref travelled with the repo, else the C
+restatement; every comparison is bit for bit.
+"""
+import numpy as np
+import pytest
+
+from util import uniform_below
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def dev(a, device="cuda"):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64)).to(device)
+
+
+def host(t):
+    return t.cpu().numpy().view(np.uint64)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda(hb):
+    if not torch.cuda.is_available() or hb.device_count() == 0:
+        pytest.fail("gpu-marked test collected on a machine without CUDA")
+
+
+def _c4_case(hb, checker, group):
+    n = 1 << 17
+    mods = hb.GeneratePrimes(16, 60, True, n)
+    assert len(set(mods)) == 16 and all((1 << 60) < q < (1 << 61) for q in mods)
+    ntts = [hb.NTT(n, q) for q in mods]
+    sz = n * group
+    a = np.concatenate([uniform_below(41 * i + 1, sz, q) for i, q in enumerate(mods)])
+    b = np.concatenate([uniform_below(41 * i + 2, sz, q) for i, q in enumerate(mods)])
+    conv = np.concatenate([
+        checker.ntt_inverse(checker.mult_mod(checker.ntt_forward(a[i * sz:(i + 1) * sz], n, q),
+                                             checker.ntt_forward(b[i * sz:(i + 1) * sz], n, q), q), n, q)
+        for i, q in enumerate(mods)])
+    return n, mods, ntts, a, b, conv
+
+
+def test_c4_poly_multiply_16_moduli_n17(hb, checker):
+    """north_star configs[3]: the whole product pipeline as one call, device and host pointers, and as
+    the three separate calls a caller of the reference would make (multi-modulus launches)."""
+    group = 2
+    n, mods, ntts, a, b, conv = _c4_case(hb, checker, group)
+    da, db = dev(a), dev(b)
+    o = torch.zeros_like(da)
+    hb.PolyMultiplyMulti(ntts, o, da, db, group)
+    assert (host(o) == conv).all()
+    assert (host(da) == a).all() and (host(db) == b).all()
+    # the unfused sequence: lazy forward transforms feed EltwiseMultMod(in_mf 4), as in dyadic-multiply / key-switch
+    fa, fb = torch.zeros_like(da), torch.zeros_like(da)
+    hb.ComputeForwardMulti(ntts, fa, da, 1, 4, batch_per_modulus=group)
+    hb.ComputeForwardMulti(ntts, fb, db, 1, 4, batch_per_modulus=group)
+    hb.EltwiseMultModMulti(fa, fa, fb, n * group, mods, 4)
+    hb.ComputeInverseMulti(ntts, fa, fa, 1, 1, batch_per_modulus=group)
+    assert (host(fa) == conv).all()
+    # host pointers (an unmodified caller): pageable numpy buffers
+    h = np.zeros_like(a)
+    hb.PolyMultiplyMulti(ntts, h, a, b, group)
+    assert (h == conv).all()
+    # per-modulus calls through the single-modulus entry points give the same bits
+    q = mods[5]
+    lo, hi = 5 * n * group, 6 * n * group
+    t = hb.NTT(n, q)
+    x, y = dev(a[lo:hi]), dev(b[lo:hi])
+    t.ComputeForward(x, x, 1, 4)
+    t.ComputeForward(y, y, 1, 4)
+    hb.EltwiseMultMod(x, x, y, n * group, q, 4)
+    t.ComputeInverse(x, x, 1, 1)
+    assert (host(x) == conv[lo:hi]).all()
+
+
+def _c5_case(hb, n, decomp, bits, kcc=2):
+    kms = rns = decomp + 1
+    mods = hb.GeneratePrimes(kms, bits, True, n)
+    t_target = np.concatenate([uniform_below(30 + j, n, mods[j]) for j in range(decomp)])
+    keys = [np.concatenate([uniform_below(1000 * j + 37 * k + i, n, mods[i]) for k in range(kcc) for i in range(kms)])
+            for j in range(decomp)]
+    result = np.concatenate([uniform_below(5000 + 100 * k + i, n, mods[i]) for k in range(kcc) for i in range(decomp)])
+    modswitch = [hb.InverseMod(mods[-1] % mods[i], mods[i]) for i in range(decomp)]
+    return kms, rns, kcc, mods, t_target, keys, result, modswitch
+
+
+def test_c5_key_switch_30_moduli_n15(hb, checker):
+    """north_star configs[4]: N = 2^15, L = 30 (29 digits + special prime), 50-bit primes."""
+    n, decomp = 1 << 15, 29
+    kms, rns, kcc, mods, t_target, keys, result, modswitch = _c5_case(hb, n, decomp, 50)
+    exp = checker.key_switch(result.copy(), t_target, n, decomp, kms, rns, kcc, mods, keys, modswitch)
+    dres = dev(result)
+    hb.KeySwitch(dres, dev(t_target), n, decomp, kms, rns, kcc, mods, [dev(x) for x in keys], modswitch)
+    assert (host(dres) == exp).all()
+    # host pointers
+    res = result.copy()
+    hb.KeySwitch(res, t_target, n, decomp, kms, rns, kcc, mods, keys, modswitch)
+    assert (res == exp).all()
+
+
+def test_c5_key_switch_60_bit_moduli(hb, checker):
+    """the same shape class with 60-bit primes (WIDE-mode transforms inside the composite), fewer digits"""
+    n, decomp = 1 << 15, 9
+    kms, rns, kcc, mods, t_target, keys, result, modswitch = _c5_case(hb, n, decomp, 60)
+    exp = checker.key_switch(result.copy(), t_target, n, decomp, kms, rns, kcc, mods, keys, modswitch)
+    dres = dev(result)
+    hb.KeySwitch(dres, dev(t_target), n, decomp, kms, rns, kcc, mods, [dev(x) for x in keys], modswitch)
+    assert (host(dres) == exp).all()
+
+
+# ------------------------------------------------ hexl_b200_set_host_devices: the host-side batch split
+def _host_split_cases(hb, checker):
+    """(name, run(), expected) for batched host-pointer calls whose unit counts do not divide evenly"""
+    n = 1 << 12
+    q = hb.GeneratePrimes(1, 55, True, n)[0]
+    t = hb.NTT(n, q)
+    batch = 37
+    x = uniform_below(77, n * batch, q)
+    yield "ntt_forward", (lambda: t.ComputeForward(np.zeros_like(x), x, 1, 1)), checker.ntt_forward(x, n, q)
+    yield "ntt_inverse", (lambda: t.ComputeInverse(np.zeros_like(x), x, 1, 1)), checker.ntt_inverse(x, n, q)
+    big = 3 * (4 << 20) + 12345  # elements: several 32 MiB staging chunks per device
+    q2 = hb.GeneratePrimes(1, 60, True, 1)[0]
+    a, b = uniform_below(5, big, q2), uniform_below(6, big, q2)
+    yield "mult_mod", (lambda: hb.EltwiseMultMod(np.zeros_like(a), a, b, big, q2, 1)), checker.mult_mod(a, b, q2, 1)
+    yield "fma_mod", (lambda: hb.EltwiseFMAMod(np.zeros_like(a), a, 12345, b, big, q2, 1)), checker.fma_mod(a, 12345, b, q2, 1)
+    yield "reduce_mod", (lambda: hb.EltwiseReduceMod(np.zeros_like(a), a, big, q2 >> 3, q2 >> 3, 1)), a % np.uint64(q2 >> 3)
+
+
+def test_set_host_devices_single_and_repeated_device(hb, checker):
+    """Runs on any box: the split over [0] and over [0, 0] (two blocks on one GPU, sharing its staging
+    streams) must give the single-device bits."""
+    try:
+        for devices in ([0], [0, 0], [0, 0, 0]):
+            hb.set_host_devices(devices)
+            for name, run, exp in _host_split_cases(hb, checker):
+                assert (run() == exp).all(), (devices, name)
+    finally:
+        hb.set_host_devices([])
+    with pytest.raises(hb.HexlB200Error):
+        hb.set_host_devices([hb.device_count()])  # out of range
+
+
+def test_set_host_devices_across_gpus(hb, checker):
+    """Two or more GPUs: contiguous blocks of whole units per device, bit-identical to one device;
+    the per-device twiddle tables are uploaded on first use on each device."""
+    ndev = hb.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least 2 GPUs")
+    try:
+        for devices in (list(range(ndev)), [1, 0], list(range(ndev))[::-1]):
+            hb.set_host_devices(devices)
+            for name, run, exp in _host_split_cases(hb, checker):
+                assert (run() == exp).all(), (devices, name)
+        # composites take the same split (RNS moduli / ciphertext components are independent units)
+        n, mods, ntts, a, b, conv = _c4_case(hb, checker, 1)
+        hb.set_host_devices(list(range(ndev)))
+        h = np.zeros_like(a)
+        hb.PolyMultiplyMulti(ntts, h, a, b, 1)
+        assert (h == conv).all()
+    finally:
+        hb.set_host_devices([])
+    # device pointers on a GPU other than the current one: tables follow the data
+    n = 1 << 13
+    q = hb.GeneratePrimes(1, 50, True, n)[0]
+    t = hb.NTT(n, q)
+    x = uniform_below(9, n * 3, q)
+    with torch.cuda.device(1):
+        d = dev(x, "cuda:1")
+        t.ComputeForward(d, d, 1, 1)
+        torch.cuda.synchronize()
+    assert (host(d) == checker.ntt_forward(x, n, q)).all()

@@ -26,7 +26,7 @@ def host(t):
 
 for logn in (12, 14, 15, 16, 17):
     n = 1 << logn
-    for bits in (29, 50, 60, 61):
+    for bits in (29, 33, 50, 55, 60, 61):
         q = hb.GeneratePrimes(1, bits, True, n)[0]
         t = hb.NTT(n, q)
         batch = 5
@@ -43,4 +43,22 @@ for logn in (12, 14, 15, 16, 17):
         t.ComputeForward(d, d, 1, 1)
         t.ComputeInverse(d, d, 1, 1)
         assert (host(d) == x).all(), ("round trip in place", logn, bits)
+# extreme inputs: every coefficient at the top of its allowed range (largest lazy growth inside the kernels)
+for logn, bits in ((12, 55), (16, 55), (16, 33), (17, 50), (20, 55)):
+    n = 1 << logn
+    q = hb.GeneratePrimes(1, bits, True, n)[0]
+    t = hb.NTT(n, q)
+    for in_mf in (1, 4):
+        x = np.full(n * 2, q * in_mf - 1, dtype=np.uint64)
+        x[n:] = uniform_below(logn, n, q * in_mf)
+        x[n] = 0
+        o = dev(np.zeros_like(x))
+        t.ComputeForward(o, dev(x), in_mf, 1)
+        assert (host(o) == checker.ntt_forward(x, n, q, in_mf, 1)).all(), ("fwd extreme", logn, bits, in_mf)
+    for in_mf in (1, 2):
+        x = np.full(n * 2, q * in_mf - 1, dtype=np.uint64)
+        x[n:] = uniform_below(logn + 1, n, q * in_mf)
+        o = dev(np.zeros_like(x))
+        t.ComputeInverse(o, dev(x), in_mf, 1)
+        assert (host(o) == checker.ntt_inverse(x, n, q, in_mf, 1)).all(), ("inv extreme", logn, bits, in_mf)
 print("variant ok", {k: v for k, v in os.environ.items() if k.startswith("HEXL_B200_")})

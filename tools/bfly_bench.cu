@@ -140,6 +140,93 @@ __device__ __forceinline__ void bf9(u64& X, u64& Y, const TwD& w, const Mod& m) 
   Y = X + m.four_q - T; X = X + T;
 }
 
+// ---- variant 10: quotient cross terms as two round-down DFMAs on biased operands (round 2).
+//   A0 = 2^52 + y0, A1 = 2^52 + y1 are formed by pairing a word with the constant 0x43300000 (no arithmetic);
+//   u = fma.rm(A0, beta1, K), R = fma.rm(A1, beta0, u) = 2^52 + 2 + cross - [0,2), K = 2^52 + 2 - 2^20 (b0 + b1),
+//   beta_i = b_i / 2^32;  Q + C = y1*b1 + bits(R) with C = 0x4330000000000002, and C*q is folded into the
+//   accumulator of the first product of the mad chain (m.bias).  Q is low by at most 2, as in v5.
+struct TwH { u64 w; double beta0, beta1, K; unsigned b1; };
+struct ModH { u64 q, four_q; unsigned n0, n1; u64 bias; };
+__device__ __forceinline__ double fma_rm(double a, double b, double c) {
+  double r; asm("fma.rm.f64 %0, %1, %2, %3;" : "=d"(r) : "d"(a), "d"(b), "d"(c)); return r;
+}
+__device__ __forceinline__ void bf10(u64& X, u64& Y, const TwH& w, const ModH& m) {
+  unsigned y0, y1; split(Y, y0, y1);
+  const double A0 = __hiloint2double(0x43300000, (int)y0), A1 = __hiloint2double(0x43300000, (int)y1);
+  const double R = fma_rm(A1, w.beta0, fma_rm(A0, w.beta1, w.K));
+  const u64 Qc = madwide(y1, w.b1, (u64)__double_as_longlong(R));
+  unsigned w0, w1, q0, q1, t0, t1;
+  split(w.w, w0, w1); split(Qc, q0, q1);
+  split(madwide(q0, m.n0, madwide(y0, w0, m.bias)), t0, t1);
+  t1 = madlo(y0, w1, t1); t1 = madlo(y1, w0, t1); t1 = madlo(q0, m.n1, t1); t1 = madlo(q1, m.n0, t1);
+  const u64 T = join2(t0, t1);
+  Y = X + m.four_q - T; X = X + T;
+}
+// ---- variant 11: as v10 but the operand words are converted with I2F.F64.U32 (conversion unit) instead of
+//   being paired with a constant register (which costs a MOV per word): K is then the constant 2^52 + 2.
+__device__ __forceinline__ void bf11(u64& X, u64& Y, const TwH& w, const ModH& m) {
+  unsigned y0, y1; split(Y, y0, y1);
+  const double R = fma_rm(__uint2double_rn(y1), w.beta0, fma_rm(__uint2double_rn(y0), w.beta1, 4503599627370498.0));
+  const u64 Qc = madwide(y1, w.b1, (u64)__double_as_longlong(R));
+  unsigned w0, w1, q0, q1, t0, t1;
+  split(w.w, w0, w1); split(Qc, q0, q1);
+  split(madwide(q0, m.n0, madwide(y0, w0, m.bias)), t0, t1);
+  t1 = madlo(y0, w1, t1); t1 = madlo(y1, w0, t1); t1 = madlo(q0, m.n1, t1); t1 = madlo(q1, m.n0, t1);
+  const u64 T = join2(t0, t1);
+  Y = X + m.four_q - T; X = X + T;
+}
+template <int MINB, int VAR = 10>
+__global__ void __launch_bounds__(256, MINB) kern10(u64* out, const Tw* tw, Mod m0, int iters) {
+  auto bfx = [](u64& X, u64& Y, const TwH& w, const ModH& m) { if (VAR == 10) bf10(X, Y, w, m); else bf11(X, Y, w, m); };
+  u64 v[16];
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = (u64)tid * 0x9E3779B97F4A7C15ull + e * 0x1234567ull;
+  ModH m; m.q = m0.q; m.four_q = m0.four_q; m.n0 = m0.n0; m.n1 = m0.n1; m.bias = 0x4330000000000002ull * m0.q;
+  TwH w[8];
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    Tw t = tw[(tid + g) & 1023];
+    w[g].w = t.w; w[g].b1 = hi32(t.wp);
+    w[g].beta0 = (double)lo32(t.wp) * (1.0 / 4294967296.0); w[g].beta1 = (double)hi32(t.wp) * (1.0 / 4294967296.0);
+    w[g].K = 4503599627370498.0 - 1048576.0 * ((double)lo32(t.wp) + (double)hi32(t.wp));
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int l = 0; l < 8; ++l) bfx(v[l], v[l | 8], w[0], m);
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int l = 0; l < 4; ++l) bfx(v[(g << 3) | l], v[((g << 3) | l) | 4], w[g], m);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int l = 0; l < 2; ++l) bfx(v[(g << 2) | l], v[((g << 2) | l) | 2], w[g], m);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) bfx(v[g << 1], v[(g << 1) | 1], w[g], m);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] &= (1ull << 60) - 1;
+  }
+  u64 acc = 0;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc ^= v[e];
+  out[tid] = acc;
+}
+template <int MINB, int VAR = 10> void run10(const char* name, u64* out, const Tw* tw, Mod m, int blocks_per_sm) {
+  const int iters = 2000, grid = 148 * blocks_per_sm;
+  kern10<MINB, VAR><<<grid, 256>>>(out, tw, m, 10);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  cudaEventRecord(a);
+  kern10<MINB, VAR><<<grid, 256>>>(out, tw, m, iters);
+  cudaEventRecord(b); cudaEventSynchronize(b);
+  float ms; cudaEventElapsedTime(&ms, a, b);
+  double bfl = (double)grid * 256 * iters * 32;
+  cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern10<MINB, VAR>);
+  printf("%-28s blocks/SM %d regs %3d : %8.1f G bfly/s = %6.3f M NTT(2^16)/s = %5.1f SMSP-cycles per warp-bfly  %s\n", name,
+         blocks_per_sm, fa.numRegs, bfl / ms / 1e6, bfl / ms / 1e6 / 524288.0 * 1e3, 592.0 * 1.965e9 / (bfl / ms * 1e3 / 32),
+         cudaGetErrorString(cudaGetLastError()));
+}
+
 template <int V> __device__ __forceinline__ void bf(u64& X, u64& Y, Tw w, const Mod& m) {
   if (V == 5) { bf5(X, Y, w, m); return; } if (V == 6) { bf6(X, Y, w, m); return; }
   if (V == 7) { bf7(X, Y, w, m); return; } if (V == 8) { bf8(X, Y, w, m); return; }
@@ -262,6 +349,14 @@ int main() {
   run9<2>("v9 fp64 cross terms", out, tw, m, 2);
   run9<2>("v9 fp64 cross terms", out, tw, m, 3);
   run9<3>("v9 mb3", out, tw, m, 3);
+  run10<2>("v10 fp64 biased 2xDFMA", out, tw, m, 2);
+  run10<2>("v10 fp64 biased 2xDFMA", out, tw, m, 3);
+  run10<3>("v10 mb3", out, tw, m, 3);
+  run10<3>("v10 mb3 x4", out, tw, m, 4);
+  run10<2, 11>("v11 fp64 I2F 2xDFMA", out, tw, m, 2);
+  run10<2, 11>("v11 fp64 I2F 2xDFMA", out, tw, m, 3);
+  run10<3, 11>("v11 mb3", out, tw, m, 3);
+  run10<3, 11>("v11 mb3 x4", out, tw, m, 4);
   run<5, 3>("v5 mb3", out, tw, m, 3);
   run<6, 3>("v6 mb3", out, tw, m, 3);
   run<7, 3>("v7 mb3", out, tw, m, 3);
