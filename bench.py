@@ -20,6 +20,14 @@ are the barrier and the max-over-ranks of the measured time.
            against the measured HBM copy bandwidth; 16*N algorithmic bytes/NTT.
 `cpu_baseline`: the compiled reference (oracle/_ref) timed on the host cores
            (rank 0, N = 1 only), on a bounded sample of the same workload.
+`eltwise` : BASELINE configs[2]: EltwiseMultMod / FMAMod / ReduceMod over N = 2^10..2^17 x {40,50,60}-bit q,
+           batch 4096, algorithmic GB/s and fraction of the measured HBM peak.
+`c4`      : BASELINE configs[3]: FwdNTT -> EltwiseMultMod -> InvNTT, N = 2^17, 16 x 60-bit moduli, the moduli
+           split across the ranks (2 per GPU at 8 GPUs; strong scaling of one fixed job), residue products/s.
+`c5`      : BASELINE configs[4]: CKKS KeySwitch, N = 2^15, 30 RNS moduli, sharded by ciphertext (every rank holds
+           the keys and switches its own ciphertexts: no exchange on the data path), key switches/s; `e2e` =
+           host buffers through hexl_b200_key_switch_resident with the keys resident on the GPU.
+Every rank is bound to the NUMA node of its GPU before it allocates pinned memory.
 """
 from __future__ import annotations
 
@@ -54,6 +62,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-eltwise", action="store_true")
+    ap.add_argument("--no-composites", action="store_true", help="skip the c4 / c5 legs")
+    ap.add_argument("--e2e-steps", type=int, default=None)
     return ap.parse_args()
 
 
@@ -100,6 +110,44 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ NUMA
+def bind_to_gpu_numa(local: int):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, so that pinned staging buffers are allocated
+    (first touch) in that node's DRAM and H2D/D2H copies do not cross the socket interconnect.  Returns a short
+    description for the JSON line; a no-op on single-node hosts or when sysfs does not say."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read())
+        if node < 0:
+            return {"node": None, "note": "sysfs reports no NUMA affinity"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return {"node": node, "note": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed)}
+    except (OSError, ValueError, AttributeError, RuntimeError) as e:
+        return {"node": None, "note": f"not bound ({type(e).__name__})"}
+
+
+def source_hash() -> str:
+    """sha256 over the kernel sources: profiles/traffic.json is only believed when it was captured on this code"""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "hexl_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh", ".h", ".cpp")):
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
 
 
 # ------------------------------------------------------------ reference arm
@@ -211,6 +259,196 @@ def whole_job_value(units_per_rank: int, world: int, seconds: float, weak: bool 
 
 
 # ----------------------------------------------------------------- b200 arm
+def gpu_time_ms(torch, fn, reps, sync):
+    """device time of `reps` back-to-back calls of fn (CUDA events on the current stream), per call"""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def eltwise_sweep(hb, torch, peak, gen, sync):
+    """BASELINE configs[2]: N = 2^10..2^17 x q in {40,50,60}-bit x {MultMod, FMAMod, ReduceMod}, batch 4096"""
+    out = {"batch": 4096, "bytes_per_element": {"mult_mod": 24, "fma_mod": 24, "reduce_mod": 16}, "points": []}
+    fracs = []
+    cap = 4096 << 17
+    a = torch.empty(cap, dtype=torch.int64, device="cuda")
+    b = torch.empty(cap, dtype=torch.int64, device="cuda")
+    r = torch.empty(cap, dtype=torch.int64, device="cuda")
+    for bits in (40, 50, 60):
+        for logn in range(10, 18):
+            n = 4096 << logn
+            q = hb.GeneratePrimes(1, bits, True, 1 << logn)[0]
+            av, bv, rv = a[:n], b[:n], r[:n]
+            av.random_(0, q, generator=gen)
+            bv.random_(0, q, generator=gen)
+            ops = {"mult_mod": (24, lambda: hb.EltwiseMultMod(rv, av, bv, n, q, 1)),
+                   "fma_mod": (24, lambda: hb.EltwiseFMAMod(rv, av, 123456789 % q, bv, n, q, 1)),
+                   "reduce_mod": (16, lambda: hb.EltwiseReduceMod(rv, av, n, q, q, 1))}
+            row = {"logn": logn, "q_bits": bits}
+            for name, (bpe, fn) in ops.items():
+                fn(); fn()
+                reps = 3 if logn >= 15 else 8
+                ms = gpu_time_ms(torch, fn, reps, sync)
+                gbs = bpe * n / (ms * 1e-3) / 1e9
+                row[name] = round(gbs, 1)
+                fracs.append(gbs / peak)
+            out["points"].append(row)
+    out["frac_of_hbm_peak"] = {"min": min(fracs), "median": statistics.median(fracs), "max": max(fracs)}
+    # the single largest point, kept under the round-1 key names
+    big = out["points"][-1]
+    for name in ("mult_mod", "fma_mod", "reduce_mod"):
+        out[name] = {"GBps": big[name], "frac_of_hbm_peak": big[name] / peak}
+    return out
+
+
+def c4_leg(args, hb, torch, rank, world, gen, sync, peak, cpu_ok):
+    """configs[3]: N = 2^17, 16 x 60-bit moduli split across the ranks, `group` polynomials per modulus"""
+    n, nmod, group = 1 << 17, 16, 32
+    mods_all = hb.GeneratePrimes(nmod, 60, True, n)
+    lo, hi = nmod * rank // world, nmod * (rank + 1) // world
+    mods = mods_all[lo:hi]
+    ntts = [hb.NTT(n, q) for q in mods]
+    sz = n * group
+    a = torch.empty(len(mods) * sz, dtype=torch.int64, device="cuda")
+    b = torch.empty_like(a)
+    for i, q in enumerate(mods):
+        a[i * sz:(i + 1) * sz].random_(0, q, generator=gen)
+        b[i * sz:(i + 1) * sz].random_(0, q, generator=gen)
+    r = torch.empty_like(a)
+    fn = lambda: hb.PolyMultiplyMulti(ntts, r, a, b, group)
+    fn(); fn()
+    ms = max_over_ranks(gpu_time_ms(torch, fn, 5, sync), world)
+    out = {"workload": f"FwdNTT x2 -> EltwiseMultMod -> InvNTT, N=2^17, {nmod} x 60-bit moduli, {group} polynomials per modulus",
+           "value": nmod * group / (ms * 1e-3), "unit": "residue products/s", "ms_per_call": ms, "scaling": "strong",
+           "moduli_per_rank": [nmod * (k + 1) // world - nmod * k // world for k in range(world)],
+           "algorithmic_bytes_per_product": 72 * n,
+           "hbm_GBps_per_gpu": 72.0 * n * len(mods) * group / (ms * 1e-3) / 1e9,
+           "limit": "integer-multiply pipe of the three transforms (no inter-GPU traffic: each rank owns whole moduli)"}
+    out["frac_of_hbm_peak"] = out["hbm_GBps_per_gpu"] / peak
+    # end to end: pageable-free pinned host buffers through the chunked staging path of the same call
+    try:
+        ha, hbuf, hr = (hb.pinned_empty(a.numel()) for _ in range(3))
+        ha[:] = a.cpu().numpy().view("uint64")
+        hbuf[:] = b.cpu().numpy().view("uint64")
+        efn = lambda: hb.PolyMultiplyMulti(ntts, hr, ha, hbuf, group)
+        efn()
+        assert (hr == r.cpu().numpy().view("uint64")).all(), "c4 host path differs from the device path"
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            efn()
+        dt = max_over_ranks((time.perf_counter() - t0) / 3, world)
+        out["e2e"] = {"value": nmod * group / dt, "unit": "residue products/s", "h2d_bytes_per_step": 16 * a.numel(),
+                      "d2h_bytes_per_step": 8 * a.numel(), "ms_per_call": dt * 1e3,
+                      "h2d_GBps_per_gpu": 16 * a.numel() / dt / 1e9}
+        for buf in (ha, hbuf, hr):
+            hb.pinned_free(buf)
+    except hb.HexlB200Error as e:
+        out["e2e"] = {"unavailable": str(e)[:120]}
+    if cpu_ok:
+        import numpy as np
+        import oracle
+        chk = oracle.best_checker()
+        threads = cpu_threads()
+        q = mods_all[0]
+        polys = max(threads, 8)
+        x = np.random.default_rng(1).integers(0, q, size=n * polys, dtype=np.uint64)
+        y = np.random.default_rng(2).integers(0, q, size=n * polys, dtype=np.uint64)
+
+        def cpu():
+            fx = chk.ntt_forward(x, n, q, 1, 4, threads=threads)
+            fy = chk.ntt_forward(y, n, q, 1, 4, threads=threads)
+            p = chk.mult_mod(fx, fy, q, 4, rows=polys, threads=threads)
+            return chk.ntt_inverse(p, n, q, 1, 1, threads=threads)
+        cpu()
+        t0 = time.perf_counter()
+        ref = cpu()
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": polys / dt, "unit": "residue products/s", "cores": threads, "kind": chk.kind,
+                               "sample": f"{polys} polynomials of one modulus"}
+        # parity of the timed device result against the reference on the first polynomial of the first modulus
+        x0 = a[:n].cpu().numpy().view("uint64"); y0 = b[:n].cpu().numpy().view("uint64")
+        exp = chk.ntt_inverse(chk.mult_mod(chk.ntt_forward(x0, n, q), chk.ntt_forward(y0, n, q), q), n, q)
+        out["parity"] = bool((r[:n].cpu().numpy().view("uint64") == exp).all())
+        assert out["parity"], "c4 device result differs from the checker"
+    return out
+
+
+def c5_leg(args, hb, torch, rank, world, gen, sync, cpu_ok):
+    """configs[4]: CKKS KeySwitch, N = 2^15, 30 moduli (29 digits + special prime), sharded by ciphertext"""
+    import numpy as np
+    n, decomp, kcc, cts = 1 << 15, 29, 2, 8
+    kms = rns = decomp + 1
+    mods = hb.GeneratePrimes(kms, 50, True, n)
+    modswitch = [hb.InverseMod(mods[-1] % mods[i], mods[i]) for i in range(decomp)]
+
+    def rand_rows(count_rows, row_mods):  # rows of n values, row i below row_mods[i]
+        t = torch.empty(count_rows * n, dtype=torch.int64, device="cuda")
+        for i, q in enumerate(row_mods):
+            t[i * n:(i + 1) * n].random_(0, q, generator=gen)
+        return t
+    keys = [rand_rows(kcc * kms, [mods[i] for _ in range(kcc) for i in range(kms)]) for _ in range(decomp)]
+    t_all = torch.cat([rand_rows(decomp, mods[:decomp]) for _ in range(cts)])
+    r0 = torch.cat([rand_rows(kcc * decomp, [mods[i] for _ in range(kcc) for i in range(decomp)]) for _ in range(cts)])
+    handle = hb.KeySwitchKeys(keys, n, decomp, kms, kcc)
+    res = r0.clone()
+    fn = lambda: hb.KeySwitchResident(res, t_all, n, decomp, kms, rns, kcc, mods, handle, modswitch, cts)
+    fn(); fn()
+    ms = max_over_ranks(gpu_time_ms(torch, fn, 3, sync), world)
+    out = {"workload": f"CKKS KeySwitch, N=2^15, L={kms} 50-bit moduli ({decomp} digits + special prime), "
+                       f"{cts} ciphertexts per GPU per call, keys resident ({decomp * kcc * kms * n * 8 >> 20} MiB)",
+           "value": world * cts / (ms * 1e-3), "unit": "key switches/s", "ms_per_key_switch": ms / cts, "scaling": "weak",
+           "sharding": "by ciphertext (every rank holds the keys; no exchange on the data path). Sharding one key switch "
+                       "by modulus would need the all-gather of the decomposed digits (key-switch-internal.cpp:60-131)"}
+    # end to end: host buffers in and out, keys stay on the GPU
+    try:
+        ht, hr = hb.pinned_empty(t_all.numel()), hb.pinned_empty(r0.numel())
+        ht[:] = t_all.cpu().numpy().view("uint64")
+        r0h = r0.cpu().numpy().view("uint64")
+        hr[:] = r0h
+        efn = lambda: hb.KeySwitchResident(hr, ht, n, decomp, kms, rns, kcc, mods, handle, modswitch, cts)
+        efn()
+        res.copy_(r0); fn(); torch.cuda.synchronize()
+        assert (hr == res.cpu().numpy().view("uint64")).all(), "c5 host path differs from the device path"
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            efn()
+        dt = max_over_ranks((time.perf_counter() - t0) / 3, world)
+        out["e2e"] = {"value": world * cts / dt, "unit": "key switches/s", "ms_per_key_switch": dt * 1e3 / cts,
+                      "h2d_bytes_per_step": 8 * (t_all.numel() + r0.numel()), "d2h_bytes_per_step": 8 * r0.numel()}
+        hb.pinned_free(ht); hb.pinned_free(hr)
+    except hb.HexlB200Error as e:
+        out["e2e"] = {"unavailable": str(e)[:120]}
+    if cpu_ok:
+        import oracle
+        chk = oracle.best_checker()
+        if getattr(chk, "has_seal", True):
+            hk = [k.cpu().numpy().view("uint64") for k in keys]
+            t1 = t_all[:decomp * n].cpu().numpy().view("uint64")
+            r1 = r0[:kcc * decomp * n].cpu().numpy().view("uint64")
+            threads = cpu_threads()
+            results = [None] * threads
+
+            def work(i):
+                results[i] = chk.key_switch(r1.copy(), t1, n, decomp, kms, rns, kcc, mods, hk, modswitch)
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+            [t.start() for t in th]; [t.join() for t in th]
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": threads / dt, "unit": "key switches/s", "cores": threads, "kind": chk.kind,
+                                   "sample": f"{threads} independent key switches, one per thread (the reference's KeySwitch is single-threaded)"}
+            res.copy_(r0); fn(); torch.cuda.synchronize()
+            out["parity"] = bool((res[:kcc * decomp * n].cpu().numpy().view("uint64") == results[0]).all())
+            assert out["parity"], "c5 device result differs from the checker"
+    return out
+
+
 def run_b200_arm(args):
     import numpy as np
     import torch
@@ -224,6 +462,8 @@ def run_b200_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the b200 arm has no CPU fallback)")
     torch.cuda.set_device(local)
+    affinity0 = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa(local)
     # stdout is reserved for the one JSON line: libraries that print there (NCCL's version banner
     # does) are sent to stderr at the file-descriptor level, the line goes to the saved descriptor
     sys.stdout.flush()
@@ -292,63 +532,48 @@ def run_b200_arm(args):
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     alg_bytes = 16.0 * n * batch
     achieved = alg_bytes / (fwd_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM traffic of the same call from the committed ncu capture -- believed only if it was taken on this code
+    traffic, traffic_note = None, "no profiles/traffic.json"
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("ntt_forward_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("source_hash") == source_hash():
+            per_poly = tj.get("ntt_forward_bytes_per_polynomial")
+            traffic = per_poly * batch if per_poly else tj.get("ntt_forward_bytes_per_launch")
+            traffic_note = f"ncu capture {tj.get('tag')} on this source ({tj.get('source_hash')}), scaled to the batch"
+        else:
+            traffic_note = (f"profiles/traffic.json ({tj.get('tag')}) was captured on other kernel sources "
+                            f"({tj.get('source_hash')} != {source_hash()}): not reported")
     except (OSError, ValueError):
         pass
     roofline = {"bound": "hbm", "kernel": "hexl_b200_ntt_forward (all kernels of one call)", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": traffic_note,
                 "algorithmic_bytes_per_launch": alg_bytes, "fwd_ms": fwd_ms, "inv_ms": inv_ms,
                 "inv_achieved": alg_bytes / (inv_ms * 1e-3) / 1e9,
                 "butterflies_per_ntt": (n // 2) * args.logn}
     # The bound that actually binds 64-bit moduli: the FMA-heavy integer pipe.
     # A Shoup butterfly is >= 5 IMAD.WIDE + 4 IMAD = 31 pipe cycles per warp (measured issue
-    # intervals 4.6 / 2 cycles, tools/inst_bench.cu), one such pipe per SM sub-partition.
+    # intervals 4.6 / 2 cycles, tools/pipe_bench.cu), one such pipe per SM sub-partition.
     if q >= (1 << 30):
         sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-        sm_hz = 1965.0e6  # max SM clock of this pool's B200s (the clocks line reports the one seen under load)
-        peak_bf = sms * 4 * 32 * sm_hz / 31.0
+        sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        peak_bf = sms * 4 * 32 * sm_mhz * 1e6 / 31.0
         ach_bf = batch * (n // 2) * args.logn / (fwd_ms * 1e-3)
         roofline["secondary"] = {"bound": "int-multiply pipe (IMAD/IMAD.WIDE)", "achieved": ach_bf / 1e9,
                                  "peak": peak_bf / 1e9, "unit": "G butterflies/s", "frac": ach_bf / peak_bf,
-                                 "model": "148 SMs x 4 sub-partitions x 32 lanes x 1.965 GHz / 31 pipe cycles per warp-butterfly"}
+                                 "model": f"{sms} SMs x 4 sub-partitions x 32 lanes x {sm_mhz:.0f} MHz (sampled under load) "
+                                          "/ 31 pipe cycles per warp-butterfly"}
 
-    # ---- eltwise kernels (BASELINE configs[2]): algorithmic GB/s at 4096 x 2^16 elements, 60-bit q
+    # ---- eltwise kernels (BASELINE configs[2])
     elt = None
-    if not args.no_eltwise:
-        en = 4096 << 16
-        eq = hb.GeneratePrimes(1, 60, True, 1 << 16)[0]
-        a = torch.randint(0, eq, (en,), dtype=torch.int64, device="cuda", generator=g)
-        b = torch.randint(0, eq, (en,), dtype=torch.int64, device="cuda", generator=g)
-        r = torch.empty_like(a)
-        ops = {
-            "mult_mod": (24, lambda: hb.EltwiseMultMod(r, a, b, en, eq, 1)),
-            "fma_mod": (24, lambda: hb.EltwiseFMAMod(r, a, 123456789, b, en, eq, 1)),
-            "reduce_mod": (16, lambda: hb.EltwiseReduceMod(r, a, en, eq, eq, 1)),
-            "add_mod": (24, lambda: hb.EltwiseAddMod(r, a, b, en, eq)),
-        }
-        elt = {"n": en, "q_bits": 60}
-        for name, (bpe, fn) in ops.items():
-            for _ in range(3):
-                fn()
-            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            s0.record()
-            for _ in range(5):
-                fn()
-            s1.record()
-            torch.cuda.synchronize()
-            gbs = bpe * en * 5 / (s0.elapsed_time(s1) * 1e-3) / 1e9
-            elt[name] = {"GBps": gbs, "frac_of_hbm_peak": gbs / peak}
-        del a, b, r
+    if not args.no_eltwise and rank == 0:
+        elt = eltwise_sweep(hb, torch, peak, g, torch.cuda.synchronize)
+    barrier()
 
-    # ---- end to end through the host-pointer path of the C ABI
+    # ---- end to end through the host-pointer path of the C ABI: the same per-GPU batch at every N
     e2e = None
     if not args.no_e2e:
-        # per-GPU batch of the host-pointer leg: the full batch on one GPU; 2048 polynomials
-        # (1 GiB per pinned buffer, ~50 ms per step) per rank when several ranks pin host memory at once
-        eb = args.e2e_batch or (batch if world == 1 else min(batch, 2048))
+        eb = args.e2e_batch or min(batch, 2048)   # 1 GiB per pinned buffer per rank
         hx = hy = hz = None
         while eb >= 64:
             try:
@@ -374,7 +599,10 @@ def run_b200_arm(args):
 
             estep()
             assert (hz == hx).all(), "e2e round trip failed"
-            esteps = max(2, min(args.steps, 5))
+            esteps = args.e2e_steps or max(3, min(args.steps, 10))
+            esampler = ClockSampler(local)
+            if rank == 0:
+                esampler.start()
             barrier()
             t0 = time.perf_counter()
             for _ in range(esteps):
@@ -382,30 +610,53 @@ def run_b200_arm(args):
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             dt = max_over_ranks(dt, world)
+            eclk = esampler.stop() if rank == 0 else None
+            link = 2 * 8 * n * eb * esteps / dt / 1e9
             e2e = {"value": whole_job_value(2 * eb * esteps, world, dt), "unit": "NTT/s",
                    "h2d_bytes_per_step": 2 * 8 * n * eb, "d2h_bytes_per_step": 2 * 8 * n * eb,
                    "batch_per_gpu": eb, "steps": esteps, "ms_per_step": 1e3 * dt / esteps,
-                   "path": "hexl_b200_ntt_forward/inverse with pinned HOST pointers (library stages H2D/kernel/D2H in 32 MiB chunks on 3 streams)"}
-            # (pinned buffers are released at process exit)
+                   "link_GBps_each_way_per_gpu": link, "clocks": eclk, "numa": numa,
+                   "path": "hexl_b200_ntt_forward/inverse with pinned HOST pointers (library stages H2D/kernel/D2H in 32 MiB chunks on 3 streams)",
+                   "bound": "PCIe: every transform moves 8N bytes in and 8N bytes out over the host link"}
+            for buf in (hx, hy, hz):
+                hb.pinned_free(buf)
+
+    # ---- the composite configurations
+    os.sched_setaffinity(0, affinity0)  # the CPU legs use every host core this process owns
+    cpu_ok = rank == 0 and world == 1 and not args.no_cpu
+    c4 = c5 = None
+    if not args.no_composites:
+        del z
+        torch.cuda.empty_cache()
+        c4 = c4_leg(args, hb, torch, rank, world, g, barrier, peak, cpu_ok)
+        barrier()
+        c5 = c5_leg(args, hb, torch, rank, world, g, barrier, cpu_ok)
+        barrier()
+        z = torch.empty_like(x)
+        ntt.ComputeInverse(z, y, 1, 1)
+        torch.cuda.synchronize()
 
     # ---- CPU baseline (rank 0, single-GPU runs only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if cpu_ok:
         threads = cpu_threads()
         polys = max(threads * 32, 128)
         v, kind, tier = cpu_leg(n, q, threads, polys, 3)
         cpu = {"value": v, "unit": "NTT/s", "cores": threads, "kind": kind,
                "sample": f"{polys} polynomials x (forward + inverse), best of 3, {threads} threads, tier {tier}"}
-        # the checker also looks at what the timed kernels produced: the first and last 4 polynomials of
-        # the device-resident forward output y and round trip z, bit for bit (outside every timed region)
+        # The checker also looks at what the timed kernels produced: 256 polynomials spread over the batch, the
+        # forward output y compared ON THE DEVICE with the reference's output bit for bit, and the round trip z
+        # (outside every timed region).
         import oracle
         chk = oracle.best_checker()
-        idx = list(range(4)) + list(range(batch - 4, batch))
-        hx = np.stack([x[i].cpu().numpy().view(np.uint64) for i in idx])
-        hy = np.stack([y[i].cpu().numpy().view(np.uint64) for i in idx])
-        hz = np.stack([z[i].cpu().numpy().view(np.uint64) for i in idx])
-        ok = bool((hy.reshape(-1) == chk.ntt_forward(hx.reshape(-1), n, q, 1, 1)).all() and (hz == hx).all())
-        cpu["parity"] = {"polynomials_checked": len(idx), "bit_exact": ok, "checker": chk.kind}
+        count = min(256, batch)
+        idx = torch.arange(count, device="cuda") * (batch // count)
+        hx = x[idx].cpu().numpy().view(np.uint64).reshape(-1)
+        exp = torch.from_numpy(chk.ntt_forward(hx, n, q, 1, 1, threads=threads).view(np.int64)).cuda().view(count, n)
+        ok = bool(torch.equal(y[idx], exp) and torch.equal(z[idx], x[idx]))
+        fold = int(torch.bitwise_xor(y[idx].view(-1)[0::2], y[idx].view(-1)[1::2]).sum().item()) & ((1 << 64) - 1)
+        cpu["parity"] = {"polynomials_checked": count, "bit_exact": ok, "checker": chk.kind,
+                         "compared": "on the device, every coefficient", "fold64_of_forward_output": fold}
         assert ok, "device results differ from the checker"
 
     if rank == 0:
@@ -418,7 +669,7 @@ def run_b200_arm(args):
                        "parallelism": f"{world} x independent shards, no data-path collective",
                        "l2": f"inputs ({8 * n * batch >> 20} MiB per buffer per GPU) exceed the 126 MB L2; no flush needed"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "eltwise": elt,
+            "eltwise": elt, "c4": c4, "c5": c5,
         }
         print(json.dumps(line), file=json_out, flush=True)
     if world > 1:

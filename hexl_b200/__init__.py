@@ -113,6 +113,10 @@ _sig("hexl_b200_ntt_get_cached", _int, [C.POINTER(_vp), _u64, _u64])
 _sig("hexl_b200_dyadic_multiply", _int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp])
 _sig("hexl_b200_key_switch", _int, [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp, _vp, _vp])
 
+_sig("hexl_b200_keys_upload", _int, [C.POINTER(_vp), _vp, _u64, _u64, _u64, _u64])
+_sig("hexl_b200_keys_release", None, [_vp])
+_sig("hexl_b200_key_switch_resident", _int, [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp, _vp, _u64, _vp])
+
 #: every symbol include/hexl_b200.h declares (checked against the header by the tests)
 EXPORTED = sorted(n for n in dir(_lib) if n.startswith("hexl_b200_"))
 
@@ -458,4 +462,42 @@ def KeySwitch(result, t_target_iter_ptr, n, decomp_modulus_size, key_modulus_siz
     _check(_lib.hexl_b200_key_switch(rp, tp, n, decomp_modulus_size, key_modulus_size, rns_modulus_size,
                                      key_component_count, mods.ctypes.data, key_ptrs, ms.ctypes.data,
                                      _stream(stream, rc or tc)))
+    return result
+
+
+class KeySwitchKeys:
+    """Key-switch keys uploaded once (hexl_b200_keys_upload): to the current device, or to every device
+    named with set_host_devices.  k_switch_keys: list of host or device buffers, each
+    key_component_count x key_modulus_size x n words."""
+
+    def __init__(self, k_switch_keys, n, decomp_modulus_size, key_modulus_size, key_component_count):
+        for k in k_switch_keys[:decomp_modulus_size]:
+            _need("k_switch_keys[j]", _buf(k)[1], key_component_count * key_modulus_size * n)
+        _need("k_switch_keys", len(k_switch_keys), decomp_modulus_size)
+        ptrs = (_vp * len(k_switch_keys))(*[_buf(k)[0] for k in k_switch_keys])
+        h = _vp()
+        _check(_lib.hexl_b200_keys_upload(C.byref(h), ptrs, n, decomp_modulus_size, key_modulus_size,
+                                          key_component_count))
+        self._h = h
+        self.shape = (n, decomp_modulus_size, key_modulus_size, key_component_count)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None:
+            _lib.hexl_b200_keys_release(h)
+
+
+def KeySwitchResident(result, t_target_iter_ptr, n, decomp_modulus_size, key_modulus_size, rns_modulus_size,
+                      key_component_count, moduli, keys: KeySwitchKeys, modswitch_factors, batch=1, stream=None):
+    """`batch` key switches against resident keys (hexl_b200_key_switch_resident): ciphertext c uses
+    result[c * kcc*decomp*n:] and t_target[c * decomp*n:]; host buffers are pipelined and split over the devices."""
+    mods = np.ascontiguousarray(moduli, dtype=np.uint64)
+    ms = np.ascontiguousarray(modswitch_factors, dtype=np.uint64)
+    rp, rn, rc = _buf(result); tp, tn, tc = _buf(t_target_iter_ptr)
+    _need("moduli", mods.size, key_modulus_size); _need("modswitch_factors", ms.size, decomp_modulus_size)
+    _need("result", rn, batch * key_component_count * decomp_modulus_size * n)
+    _need("t_target_iter_ptr", tn, batch * decomp_modulus_size * n)
+    _check(_lib.hexl_b200_key_switch_resident(rp, tp, n, decomp_modulus_size, key_modulus_size, rns_modulus_size,
+                                              key_component_count, mods.ctypes.data, keys._h, ms.ctypes.data, batch,
+                                              _stream(stream, rc or tc)))
     return result

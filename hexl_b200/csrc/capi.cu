@@ -54,6 +54,13 @@ struct hexl_b200_ntt {
   std::map<int, Dev> dev;  // device ordinal -> uploaded tables
 };
 
+// KeySwitch keys resident on the GPUs (hexl_b200_keys_upload): decomp buffers of kcc x key_modulus_size x n
+struct hexl_b200_keys {
+  std::atomic<int> refs{1};
+  uint64_t n = 0, decomp = 0, kcc = 0, kms = 0;
+  std::map<int, std::vector<uint64_t*>> dev;  // device ordinal -> decomp device buffers
+};
+
 namespace {
 
 thread_local std::string t_error;
@@ -196,10 +203,11 @@ StageCtx* stage_for(int dev) {
 
 // A host-pointer job: `total` elements, processed in chunks that are multiples
 // of `unit` elements.  a is always present; b optional; result may alias a or b.
-// launch(dev_result, dev_a, dev_b, elems, stream) enqueues the kernel(s).
+// launch(dev_result, dev_a, dev_b, off, elems, stream) enqueues the kernel(s) for the
+// elements [off, off + elems) of the whole job (`base` = offset of this device's block).
 template <class Launch>
 int run_host_on_device(int dev, u64* result, const u64* a, const u64* b, u64 total, u64 unit,
-                       Launch&& launch, bool wait) {
+                       Launch&& launch, bool wait, u64 base = 0) {
   DeviceGuard g;
   if (int rc = g.enter(dev)) return rc;
   StageCtx* st = stage_for(dev);
@@ -217,7 +225,7 @@ int run_host_on_device(int dev, u64* result, const u64* a, const u64* b, u64 tot
     cudaStream_t s = st->stream[slot];
     CU(cudaMemcpyAsync(st->buf[slot][0], a + off, bytes, cudaMemcpyHostToDevice, s));
     if (b) CU(cudaMemcpyAsync(st->buf[slot][1], b + off, bytes, cudaMemcpyHostToDevice, s));
-    cudaError_t e = launch(st->buf[slot][0], st->buf[slot][0], b ? st->buf[slot][1] : nullptr, elems, s);
+    cudaError_t e = launch(st->buf[slot][0], st->buf[slot][0], b ? st->buf[slot][1] : nullptr, base + off, elems, s);
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     CU(cudaMemcpyAsync(result + off, st->buf[slot][0], bytes, cudaMemcpyDeviceToHost, s));
   }
@@ -250,7 +258,7 @@ int run_host(u64* result, const u64* a, const u64* b, u64 total, u64 unit, MakeL
     int cur = 0;
     CU(cudaGetDevice(&cur));
     if (!devs.empty()) cur = devs[0];
-    auto launch = make(cur);
+    auto launch = make(cur, (u64)0, total);
     if (!launch.ok) return launch.rc;
     return run_host_on_device(cur, result, a, b, total, unit, launch, true);
   }
@@ -259,12 +267,12 @@ int run_host(u64* result, const u64* a, const u64* b, u64 total, u64 unit, MakeL
   int rc = 0;
   for (u64 d = 0; d < ndev && !rc; ++d) {
     const u64 lo = units * d / ndev * unit, hi = units * (d + 1) / ndev * unit;
-    auto launch = make(devs[d]);
+    auto launch = make(devs[d], lo, hi);
     if (!launch.ok) {
       rc = launch.rc;  // fall through: copies already enqueued on other devices still target `result`
       break;
     }
-    rc = run_host_on_device(devs[d], result + lo, a + lo, b ? b + lo : nullptr, hi - lo, unit, launch, false);
+    rc = run_host_on_device(devs[d], result + lo, a + lo, b ? b + lo : nullptr, hi - lo, unit, launch, false, lo);
   }
   for (u64 d = 0; d < ndev; ++d) {
     int rc2 = sync_stage(devs[d]);
@@ -461,7 +469,7 @@ struct NttLaunch {
   bool forward = true;
   int in_mf = 1, out_mf = 1;
   u64 n = 0;
-  cudaError_t operator()(u64* r, const u64* a, const u64*, u64 elems, cudaStream_t s) const {
+  cudaError_t operator()(u64* r, const u64* a, const u64*, u64 /*off*/, u64 elems, cudaStream_t s) const {
     return forward ? launch_ntt_forward(t, r, a, in_mf, out_mf, elems / n, s)
                    : launch_ntt_inverse(t, r, a, in_mf, out_mf, elems / n, s);
   }
@@ -498,7 +506,7 @@ int ntt_compute(bool forward, hexl_b200_ntt* h, uint64_t* result, const uint64_t
     if (e != cudaSuccess) return cuda_fail(e, "NTT launch");
     return finish_device_call(pi, stream);
   }
-  return run_host(result, operand, nullptr, batch * h->n, h->n, [&](int dev) {
+  return run_host(result, operand, nullptr, batch * h->n, h->n, [&](int dev, u64, u64) {
     NttLaunch L;
     L.forward = forward;
     L.in_mf = (int)in_mf;
@@ -521,7 +529,7 @@ struct EltLaunch {
   int rc = 0;
   EltOp op;
   EltParams p;
-  cudaError_t operator()(u64* r, const u64* a, const u64* b, u64 elems, cudaStream_t s) const {
+  cudaError_t operator()(u64* r, const u64* a, const u64* b, u64 /*off*/, u64 elems, cudaStream_t s) const {
     EltParams q = p;
     q.result = r;
     q.a = a;
@@ -542,7 +550,7 @@ int eltwise_dispatch(EltOp op, EltParams p, void* stream) {
     if (e != cudaSuccess) return cuda_fail(e, "eltwise launch");
     return finish_device_call(pi, stream);
   }
-  return run_host(p.result, p.a, p.b, p.n, 1, [&](int) {
+  return run_host(p.result, p.a, p.b, p.n, 1, [&](int, u64, u64) {
     EltLaunch L;
     L.op = op;
     L.p = p;
@@ -752,6 +760,91 @@ int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, ui
   return 0;
 }
 
+// Host-pointer RNS jobs (count moduli x per_mod elements, modulus m owns [m*per_mod, (m+1)*per_mod)) go through
+// the same chunked, multi-stream, multi-device staging as the single-modulus calls: a chunk [off, off + elems)
+// is cut at the modulus boundaries it contains and every piece is launched under its own modulus.
+enum class RnsJob { NttFwd, NttInv, Mult, Add, Sub, PolyMul };
+EltParams mult_params(uint64_t q, int in_mf) {
+  EltParams p{};
+  p.q = q;
+  p.in_mf = in_mf;
+  const int L = floor_log2(q) + 1;  // generalised Barrett constants, eltwise-mult-mod-internal.hpp:52-69
+  p.shift = L - 2;
+  p.mu = nt::multiply_factor(1ull << (L - 2), 64, q);
+  return p;
+}
+struct RnsSegLaunch {
+  bool ok = true;
+  int rc = 0;
+  RnsJob job = RnsJob::Mult;
+  u64 per_mod = 0, n = 1;
+  int in_mf = 1, out_mf = 1;
+  std::vector<u64> moduli;
+  std::vector<NttDeviceTables> t;  // per modulus, filled for the moduli this device touches (NTT jobs)
+  cudaError_t operator()(u64* r, const u64* a, const u64* b, u64 off, u64 elems, cudaStream_t s) const {
+    for (u64 pos = off; pos < off + elems;) {
+      const u64 m = pos / per_mod;
+      const u64 cnt = std::min(off + elems, (m + 1) * per_mod) - pos, o = pos - off;
+      cudaError_t e = cudaSuccess;
+      switch (job) {
+        case RnsJob::NttFwd: e = launch_ntt_forward(t[m], r + o, a + o, in_mf, out_mf, cnt / n, s); break;
+        case RnsJob::NttInv: e = launch_ntt_inverse(t[m], r + o, a + o, in_mf, out_mf, cnt / n, s); break;
+        case RnsJob::Mult:
+        case RnsJob::Add:
+        case RnsJob::Sub: {
+          EltParams p = job == RnsJob::Mult ? mult_params(moduli[m], in_mf) : EltParams{};
+          p.q = moduli[m];
+          p.result = r + o; p.a = a + o; p.b = b + o; p.n = cnt;
+          e = launch_eltwise(job == RnsJob::Mult ? EltOp::MultVV : (job == RnsJob::Add ? EltOp::AddVV : EltOp::SubVV), p, s);
+          break;
+        }
+        case RnsJob::PolyMul: {  // staged buffers: r == a (slot buffer 0), b = slot buffer 1; all in place
+          u64* fa = r + o;
+          u64* fb = const_cast<u64*>(b) + o;
+          if ((e = launch_ntt_forward(t[m], fa, a + o, 1, 4, cnt / n, s)) != cudaSuccess) return e;
+          if ((e = launch_ntt_forward(t[m], fb, fb, 1, 4, cnt / n, s)) != cudaSuccess) return e;
+          EltParams p = mult_params(moduli[m], 4);
+          p.result = fa; p.a = fa; p.b = fb; p.n = cnt;
+          if ((e = launch_eltwise(EltOp::MultVV, p, s)) != cudaSuccess) return e;
+          e = launch_ntt_inverse(t[m], fa, fa, 1, 1, cnt / n, s);
+          break;
+        }
+      }
+      if (e != cudaSuccess) return e;
+      pos += cnt;
+    }
+    return cudaSuccess;
+  }
+};
+
+// the launcher factory run_host wants: tables of the moduli inside [lo, hi) on device dev
+template <class Handles>
+auto rns_seg_factory(RnsJob job, const Handles& handles, const uint64_t* moduli, uint64_t count, u64 per_mod, u64 n,
+                     int in_mf, int out_mf) {
+  return [=, &handles](int dev, u64 lo, u64 hi) {
+    RnsSegLaunch L;
+    L.job = job;
+    L.per_mod = per_mod;
+    L.n = n;
+    L.in_mf = in_mf;
+    L.out_mf = out_mf;
+    L.moduli.resize(count);
+    const bool need_tables = job == RnsJob::NttFwd || job == RnsJob::NttInv || job == RnsJob::PolyMul;
+    if (need_tables) L.t.resize(count);
+    DeviceGuard g;
+    int rc = need_tables ? g.enter(dev) : 0;
+    for (uint64_t m = 0; m < count && !rc; ++m) {
+      L.moduli[m] = moduli ? moduli[m] : handles[m]->q;
+      if (need_tables && m * per_mod < hi && (m + 1) * per_mod > lo) rc = device_tables(handles[m], dev, &L.t[m]);
+    }
+    if (rc) {
+      L.ok = false;
+      L.rc = rc;
+    }
+    return L;
+  };
+}
+
 int ntt_compute_multi(bool forward, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
                       const uint64_t* operand, uint64_t in_mf, uint64_t out_mf, uint64_t group, void* stream) {
   if (!handles) return fail(HEXL_B200_ERR_INVALID_ARG, "handles == nullptr");
@@ -769,12 +862,13 @@ int ntt_compute_multi(bool forward, hexl_b200_ntt* const* handles, uint64_t coun
   PtrInfo pi;
   if (int rc = classify_all({result, operand}, &pi)) return rc;
   const uint64_t n = handles[0]->n;
-  if (pi.where == Where::Host) {  // staged path, one modulus at a time
-    for (uint64_t i = 0; i < count; ++i)
-      if (int rc = ntt_compute(forward, handles[i], result + i * group * n, operand + i * group * n, in_mf, out_mf,
-                               group, stream))
-        return rc;
-    return 0;
+  if (pi.where == Where::Host) {  // staged, chunked and (with host devices set) split across GPUs like a single-modulus call
+    if (g_debug.load())
+      for (uint64_t i = 0; i < count; ++i)
+        if (int rc = check_bounds(operand + i * group * n, group * n, handles[i]->q * in_mf, pi, "operand")) return rc;
+    return run_host(result, operand, nullptr, count * group * n, n,
+                    rns_seg_factory(forward ? RnsJob::NttFwd : RnsJob::NttInv, handles, nullptr, count, group * n, n,
+                                    (int)in_mf, (int)out_mf));
   }
   for (uint64_t i = 0; i < count; ++i)
     if (int rc = check_bounds(operand + i * group * n, group * n, handles[i]->q * in_mf, pi, "operand")) return rc;
@@ -1141,15 +1235,12 @@ static int rns_eltwise_entry(int op, uint64_t* result, const uint64_t* operand1,
       return rc;
     return finish_device_call(pi, stream);
   }
-  Scratch ws(nullptr);  // host pointers: staged whole, synchronous
-  uint64_t *d1 = nullptr, *d2 = nullptr;
-  if (int rc = ws.get(&d1, total)) return rc;
-  if (int rc = ws.get(&d2, total)) return rc;
-  CU(cudaMemcpyAsync(d1, operand1, total * 8, cudaMemcpyHostToDevice, nullptr));
-  CU(cudaMemcpyAsync(d2, operand2, total * 8, cudaMemcpyHostToDevice, nullptr));
-  if (int rc = rns_eltwise_on_device(op, d1, d1, d2, n_per_modulus, moduli, num_moduli, (int)in_mf, nullptr)) return rc;
-  CU(cudaMemcpy(result, d1, total * 8, cudaMemcpyDeviceToHost));
-  return 0;
+  struct NoHandles {
+    hexl_b200_ntt* operator[](uint64_t) const { return nullptr; }
+  } none;
+  const RnsJob job = op == kRnsMult ? RnsJob::Mult : (op == kRnsAdd ? RnsJob::Add : RnsJob::Sub);
+  return run_host(result, operand1, operand2, total, 1,
+                  rns_seg_factory(job, none, moduli, num_moduli, n_per_modulus, 1, (int)in_mf, 1));
 }
 
 int hexl_b200_eltwise_mult_mod_multi(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
@@ -1204,17 +1295,15 @@ int hexl_b200_poly_multiply_multi(hexl_b200_ntt* const* handles, uint64_t count,
     if (int rc = poly_multiply_on_device(pi.device, handles, count, result, a, b, group, (cudaStream_t)stream)) return rc;
     return finish_device_call(pi, stream);
   }
-  int cur = 0;
-  CU(cudaGetDevice(&cur));
-  Scratch ws(nullptr);
-  uint64_t *d1 = nullptr, *d2 = nullptr;
-  if (int rc = ws.get(&d1, total)) return rc;
-  if (int rc = ws.get(&d2, total)) return rc;
-  CU(cudaMemcpyAsync(d1, a, total * 8, cudaMemcpyHostToDevice, nullptr));
-  CU(cudaMemcpyAsync(d2, b, total * 8, cudaMemcpyHostToDevice, nullptr));
-  if (int rc = poly_multiply_on_device(cur, handles, count, d1, d1, d2, group, nullptr)) return rc;
-  CU(cudaMemcpy(result, d1, total * 8, cudaMemcpyDeviceToHost));
-  return 0;
+  if (g_debug.load())
+    for (uint64_t i = 0; i < count; ++i) {
+      if (int rc = check_bounds(a + i * group * n, group * n, handles[i]->q, pi, "a")) return rc;
+      if (int rc = check_bounds(b + i * group * n, group * n, handles[i]->q, pi, "b")) return rc;
+    }
+  // host pointers: every chunk of polynomials is copied in, transformed, multiplied, transformed back and
+  // copied out on one of the rotating staging streams, so the PCIe copies of one chunk hide under the
+  // kernels of the others; with host devices set the polynomials are split across the GPUs
+  return run_host(result, a, b, total, n, rns_seg_factory(RnsJob::PolyMul, handles, nullptr, count, group * n, n, 1, 1));
 }
 
 int hexl_b200_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2, uint64_t n,
@@ -1227,35 +1316,199 @@ int hexl_b200_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const 
     REQUIRE(moduli[i] > 1 && moduli[i] < (1ull << 62), "Require 1 < modulus < 2^62");
   PtrInfo pi;
   if (int rc = classify_all({result, operand1, operand2}, &pi)) return rc;
-  const size_t in_elems = 2 * n * num_moduli, out_elems = 3 * n * num_moduli;
   if (pi.where == Where::Device) {
     DeviceGuard g;
     if (int rc = g.enter(pi.device)) return rc;
     if (int rc = dyadic_on_device(result, operand1, operand2, n, moduli, num_moduli, (cudaStream_t)stream)) return rc;
     return finish_device_call(pi, stream);
   }
+  // Host pointers: blocks of moduli travel through the rotating staging slots (the layout is
+  // [polynomial][modulus][n], so a block of moduli is a 2-D copy: 2 rows in, 3 rows out).
   int cur = 0;
   CU(cudaGetDevice(&cur));
-  Scratch ws(nullptr);
-  uint64_t *d1 = nullptr, *d2 = nullptr, *dr = nullptr;
-  if (int rc = ws.get(&d1, in_elems)) return rc;
-  if (int rc = ws.get(&d2, in_elems)) return rc;
-  if (int rc = ws.get(&dr, out_elems)) return rc;
-  CU(cudaMemcpyAsync(d1, operand1, in_elems * 8, cudaMemcpyHostToDevice, nullptr));
-  CU(cudaMemcpyAsync(d2, operand2, in_elems * 8, cudaMemcpyHostToDevice, nullptr));
-  if (int rc = dyadic_on_device(dr, d1, d2, n, moduli, num_moduli, nullptr)) return rc;
-  CU(cudaMemcpy(result, dr, out_elems * 8, cudaMemcpyDeviceToHost));
+  {
+    const std::vector<int> devs = host_devices();
+    if (!devs.empty()) cur = devs[0];
+  }
+  DeviceGuard g;
+  if (int rc = g.enter(cur)) return rc;
+  StageCtx* st = stage_for(cur);
+  std::lock_guard<std::mutex> lk(st->mu);
+  if (int rc = st->init()) return rc;
+  u64 mb = std::max<u64>(1, (kChunkBytes / sizeof(u64)) / (3 * n));
+  mb = std::min<u64>({mb, (u64)kParamBlock, num_moduli});
+  const size_t row = (size_t)num_moduli * n * sizeof(u64);  // host pitch: one polynomial over all moduli
+  int slot = 0;
+  for (u64 m0 = 0; m0 < num_moduli; m0 += mb, slot = (slot + 1) % kSlots) {
+    const u64 cnt = std::min(mb, num_moduli - m0);
+    const size_t w = (size_t)cnt * n * sizeof(u64);
+    if (int rc = st->reserve(slot, 0, 3 * w)) return rc;
+    if (int rc = st->reserve(slot, 1, 2 * w)) return rc;
+    if (int rc = st->reserve(slot, 2, 2 * w)) return rc;
+    cudaStream_t sx = st->stream[slot];
+    u64 *dr = st->buf[slot][0], *d1 = st->buf[slot][1], *d2 = st->buf[slot][2];
+    CU(cudaMemcpy2DAsync(d1, w, operand1 + m0 * n, row, w, 2, cudaMemcpyHostToDevice, sx));
+    CU(cudaMemcpy2DAsync(d2, w, operand2 + m0 * n, row, w, 2, cudaMemcpyHostToDevice, sx));
+    if (int rc = dyadic_on_device(dr, d1, d2, n, moduli + m0, cnt, sx)) return rc;
+    CU(cudaMemcpy2DAsync(result + m0 * n, row, dr, w, w, 3, cudaMemcpyDeviceToHost, sx));
+  }
+  for (int k = 0; k < kSlots; ++k) CU(cudaStreamSynchronize(st->stream[k]));
   return 0;
+}
+
+// One or more key switches on HOST buffers against keys already on the devices: ciphertext c occupies
+// result[c * kcc*decomp*n ...] and t_target[c * decomp*n ...].  Each ciphertext runs on one of the rotating
+// staging streams (digits in, result in, ~12 kernels, result out), so the copies of one ciphertext overlap the
+// kernels of its neighbours; with host devices set the batch is split across the GPUs holding the keys.
+static int key_switch_host_batch(uint64_t* result, const uint64_t* t_target, uint64_t n, uint64_t decomp,
+                                 uint64_t key_modulus_size, uint64_t rns, uint64_t kcc, const uint64_t* moduli,
+                                 const hexl_b200_keys* keys, const uint64_t* modswitch, uint64_t batch) {
+  std::vector<int> devs = host_devices();
+  if (devs.empty()) {
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    devs.push_back(cur);
+  }
+  std::vector<int> use;
+  for (int d : devs)
+    if (keys->dev.count(d)) use.push_back(d);
+  if (use.empty()) return fail(HEXL_B200_ERR_INVALID_ARG, "the key handle holds no copy on the device(s) used for host calls");
+  if (use.size() > batch) use.resize(batch);
+  const u64 res_elems = kcc * decomp * n, t_elems = decomp * n;
+  int rc = 0;
+  for (size_t di = 0; di < use.size() && !rc; ++di) {
+    const int dev = use[di];
+    const u64 c_lo = batch * di / use.size(), c_hi = batch * (di + 1) / use.size();
+    DeviceGuard g;
+    if ((rc = g.enter(dev))) break;
+    StageCtx* st = stage_for(dev);
+    std::lock_guard<std::mutex> lk(st->mu);
+    if ((rc = st->init())) break;
+    const std::vector<uint64_t*>& dk = keys->dev.at(dev);
+    int slot = 0;
+    for (u64 c = c_lo; c < c_hi && !rc; ++c, slot = (slot + 1) % kSlots) {
+      if ((rc = st->reserve(slot, 0, res_elems * 8))) break;
+      if ((rc = st->reserve(slot, 1, t_elems * 8))) break;
+      cudaStream_t sx = st->stream[slot];
+      u64 *d_res = st->buf[slot][0], *d_t = st->buf[slot][1];
+      cudaError_t e = cudaMemcpyAsync(d_t, t_target + c * t_elems, t_elems * 8, cudaMemcpyHostToDevice, sx);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(d_res, result + c * res_elems, res_elems * 8, cudaMemcpyHostToDevice, sx);
+      if (e != cudaSuccess) {
+        rc = cuda_fail(e, "KeySwitch H2D");
+        break;
+      }
+      rc = key_switch_on_device(dev, d_res, d_t, n, decomp, key_modulus_size, rns, kcc, moduli, dk.data(), modswitch, sx);
+      if (rc) break;
+      e = cudaMemcpyAsync(result + c * res_elems, d_res, res_elems * 8, cudaMemcpyDeviceToHost, sx);
+      if (e != cudaSuccess) rc = cuda_fail(e, "KeySwitch D2H");
+    }
+  }
+  for (int dev : use) {
+    int rc2 = sync_stage(dev);
+    if (!rc) rc = rc2;
+  }
+  return rc;
+}
+
+static int key_switch_check(const void* result, const void* t_target, uint64_t n, uint64_t decomp,
+                            uint64_t key_modulus_size, uint64_t rns, uint64_t kcc, const uint64_t* moduli,
+                            const uint64_t* modswitch) {
+  REQUIRE(result && t_target && moduli && modswitch, "Require non-null arguments");
+  REQUIRE(n >= 2 && !(n & (n - 1)), "Require n a power of two");
+  REQUIRE(decomp >= 1 && kcc >= 1, "Require decomp_modulus_size, key_component_count >= 1");
+  REQUIRE(rns == decomp + 1, "Require rns_modulus_size == decomp_modulus_size + 1");
+  REQUIRE(key_modulus_size >= rns, "Require key_modulus_size >= rns_modulus_size");
+  return 0;
+}
+
+int hexl_b200_keys_upload(hexl_b200_keys** out, const uint64_t* const* k_switch_keys, uint64_t n,
+                          uint64_t decomp, uint64_t key_modulus_size, uint64_t kcc) {
+  REQUIRE(out && k_switch_keys, "Require out, k_switch_keys != nullptr");
+  *out = nullptr;
+  REQUIRE(n >= 1 && decomp >= 1 && kcc >= 1 && key_modulus_size >= 1, "Require non-zero sizes");
+  for (uint64_t j = 0; j < decomp; ++j) REQUIRE(k_switch_keys[j] != nullptr, "Require k_switch_keys[j] != nullptr");
+  std::vector<int> devs = host_devices();
+  if (devs.empty()) {
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    devs.push_back(cur);
+  }
+  std::sort(devs.begin(), devs.end());
+  devs.erase(std::unique(devs.begin(), devs.end()), devs.end());
+  hexl_b200_keys* k = new (std::nothrow) hexl_b200_keys();
+  if (!k) return fail(HEXL_B200_ERR_ALLOC, "out of host memory");
+  k->n = n; k->decomp = decomp; k->kcc = kcc; k->kms = key_modulus_size;
+  const size_t bytes = (size_t)kcc * key_modulus_size * n * sizeof(uint64_t);
+  int rc = 0;
+  for (int dev : devs) {
+    DeviceGuard g;
+    if ((rc = g.enter(dev))) break;
+    std::vector<uint64_t*>& v = k->dev[dev];
+    v.assign(decomp, nullptr);
+    for (uint64_t j = 0; j < decomp && !rc; ++j) {
+      cudaError_t e = cudaMalloc(&v[j], bytes);
+      if (e == cudaSuccess) e = cudaMemcpy(v[j], k_switch_keys[j], bytes, cudaMemcpyDefault);  // host or device source
+      if (e != cudaSuccess) rc = cuda_fail(e, "hexl_b200_keys_upload");
+    }
+    if (!rc) {
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) rc = cuda_fail(e, "hexl_b200_keys_upload");
+    }
+    if (rc) break;
+  }
+  if (rc) {
+    hexl_b200_keys_release(k);
+    return rc;
+  }
+  *out = k;
+  return 0;
+}
+
+void hexl_b200_keys_release(hexl_b200_keys* k) {
+  if (!k || k->refs.fetch_sub(1) != 1) return;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (auto& kv : k->dev)
+    if (cudaSetDevice(kv.first) == cudaSuccess)
+      for (uint64_t* p : kv.second) cudaFree(p);
+  if (prev >= 0) cudaSetDevice(prev);
+  cudaGetLastError();
+  delete k;
+}
+
+int hexl_b200_key_switch_resident(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n, uint64_t decomp,
+                                  uint64_t key_modulus_size, uint64_t rns, uint64_t kcc, const uint64_t* moduli,
+                                  const hexl_b200_keys* keys, const uint64_t* modswitch_factors, uint64_t batch,
+                                  void* stream) {
+  if (int rc = key_switch_check(result, t_target_iter_ptr, n, decomp, key_modulus_size, rns, kcc, moduli, modswitch_factors))
+    return rc;
+  REQUIRE(keys != nullptr, "Require keys != nullptr");
+  REQUIRE(keys->n == n && keys->decomp >= decomp && keys->kcc == kcc && keys->kms == key_modulus_size,
+          "the key handle was uploaded for another shape");
+  if (batch == 0) return 0;
+  PtrInfo pi;
+  if (int rc = classify_all({result, t_target_iter_ptr}, &pi)) return rc;
+  if (pi.where == Where::Host)
+    return key_switch_host_batch(result, t_target_iter_ptr, n, decomp, key_modulus_size, rns, kcc, moduli, keys,
+                                 modswitch_factors, batch);
+  auto it = keys->dev.find(pi.device);
+  if (it == keys->dev.end()) return fail(HEXL_B200_ERR_MIXED_POINTERS, "the key handle holds no copy on the device of result");
+  DeviceGuard g;
+  if (int rc = g.enter(pi.device)) return rc;
+  for (uint64_t c = 0; c < batch; ++c)
+    if (int rc = key_switch_on_device(pi.device, result + c * kcc * decomp * n, t_target_iter_ptr + c * decomp * n, n, decomp,
+                                      key_modulus_size, rns, kcc, moduli, it->second.data(), modswitch_factors,
+                                      (cudaStream_t)stream))
+      return rc;
+  return finish_device_call(pi, stream);
 }
 
 int hexl_b200_key_switch(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n, uint64_t decomp,
                          uint64_t key_modulus_size, uint64_t rns, uint64_t kcc, const uint64_t* moduli,
                          const uint64_t* const* k_switch_keys, const uint64_t* modswitch_factors, void* stream) {
-  REQUIRE(result && t_target_iter_ptr && moduli && k_switch_keys && modswitch_factors, "Require non-null arguments");
-  REQUIRE(n >= 2 && !(n & (n - 1)), "Require n a power of two");
-  REQUIRE(decomp >= 1 && kcc >= 1, "Require decomp_modulus_size, key_component_count >= 1");
-  REQUIRE(rns == decomp + 1, "Require rns_modulus_size == decomp_modulus_size + 1");
-  REQUIRE(key_modulus_size >= rns, "Require key_modulus_size >= rns_modulus_size");
+  if (int rc = key_switch_check(result, t_target_iter_ptr, n, decomp, key_modulus_size, rns, kcc, moduli, modswitch_factors))
+    return rc;
+  REQUIRE(k_switch_keys != nullptr, "Require non-null arguments");
   for (uint64_t j = 0; j < decomp; ++j) REQUIRE(k_switch_keys[j] != nullptr, "Require k_switch_keys[j] != nullptr");
   PtrInfo pi;
   if (int rc = classify_all({result, t_target_iter_ptr}, &pi)) return rc;
@@ -1273,27 +1526,15 @@ int hexl_b200_key_switch(uint64_t* result, const uint64_t* t_target_iter_ptr, ui
       return rc;
     return finish_device_call(pi, stream);
   }
-  int cur = 0;
-  CU(cudaGetDevice(&cur));
-  Scratch ws(nullptr);
-  const size_t res_elems = kcc * decomp * n, key_elems = kcc * key_modulus_size * n;
-  uint64_t *d_res = nullptr, *d_t = nullptr;
-  if (int rc = ws.get(&d_res, res_elems)) return rc;
-  if (int rc = ws.get(&d_t, decomp * n)) return rc;
-  std::vector<const uint64_t*> d_keys(decomp);
-  for (uint64_t j = 0; j < decomp; ++j) {
-    uint64_t* dk = nullptr;
-    if (int rc = ws.get(&dk, key_elems)) return rc;
-    CU(cudaMemcpyAsync(dk, k_switch_keys[j], key_elems * 8, cudaMemcpyHostToDevice, nullptr));
-    d_keys[j] = dk;
-  }
-  CU(cudaMemcpyAsync(d_res, result, res_elems * 8, cudaMemcpyHostToDevice, nullptr));
-  CU(cudaMemcpyAsync(d_t, t_target_iter_ptr, decomp * n * 8, cudaMemcpyHostToDevice, nullptr));
-  if (int rc = key_switch_on_device(cur, d_res, d_t, n, decomp, key_modulus_size, rns, kcc, moduli, d_keys.data(),
-                                    modswitch_factors, nullptr))
-    return rc;
-  CU(cudaMemcpy(result, d_res, res_elems * 8, cudaMemcpyDeviceToHost));
-  return 0;
+  // Host pointers, the reference's call shape (key-switch.hpp:34-39 keeps the keys in caller memory): the keys
+  // cross PCIe on every call.  A caller that switches more than once with the same keys uploads them once
+  // (hexl_b200_keys_upload) and calls hexl_b200_key_switch_resident.
+  hexl_b200_keys* tmp = nullptr;
+  if (int rc = hexl_b200_keys_upload(&tmp, k_switch_keys, n, decomp, key_modulus_size, kcc)) return rc;
+  const int rc = key_switch_host_batch(result, t_target_iter_ptr, n, decomp, key_modulus_size, rns, kcc, moduli, tmp,
+                                       modswitch_factors, 1);
+  hexl_b200_keys_release(tmp);
+  return rc;
 }
 
 }  // extern "C"

@@ -144,16 +144,17 @@ __device__ __forceinline__ Twiddle32 ld_tw(const Twiddle32* p) {
   return t;
 }
 
-// floor(a*b / 2^64) - {0,1,2}: a1*b1 + hi32(a1*b0) + hi32(a0*b1); the two high
-// halves are folded in with multiply-by-one wide mads (no ALU work at all).
+// floor(a*b / 2^64) - {0,1,2}: a1*b1 + hi32(a1*b0) + hi32(a0*b1).  The two high halves are summed first
+// (one IADD3 + IADD3.X pair, a genuine 64-bit value in a register pair) and ride in as the accumulator of
+// a1*b1.  Folding them in one at a time -- as multiply-by-one wide mads, or as two 64-bit adds -- makes
+// ptxas zero-extend a high half into a fresh register pair (MOV + IMAD.MOV/HFMA2 per butterfly, the latter
+// on the multiplier pipe that bounds these kernels).
 __device__ __forceinline__ u64 mulhi_approx(u64 a, u64 b) {
   unsigned a0, a1, b0, b1;
   split(a, a0, a1);
   split(b, b0, b1);
-  u64 Q = mul_wide(a1, b1);
-  Q = mad_wide(hi32(mul_wide(a1, b0)), 1u, Q);
-  Q = mad_wide(hi32(mul_wide(a0, b1)), 1u, Q);
-  return Q;
+  const u64 hs = (u64)hi32(mul_wide(a1, b0)) + (u64)hi32(mul_wide(a0, b1));
+  return mad_wide(a1, b1, hs);
 }
 
 // low 64 bits of x*w + Q*(2^64 - q): 2 wide and 4 narrow IMADs, no adds
@@ -277,13 +278,25 @@ __device__ __forceinline__ u64 barrett_lazy(u64 x, const Mod& m) {
   t1 = mad_lo(q1, m.n0, t1);
   return join(t0, t1);
 }
-// Same for q >= 2^32, where mu < 2^32 and the quotient is a single 32-bit word.
+// Same for q >= 2^32, where mu < 2^32 and the quotient is a single 32-bit word:
+// Q = floor(x*mu / 2^64) or one less = hi32(x1*mu + hi32(x0*mu)), the carry into the high word taken with
+// an explicit add.cc / addc pair (a 64-bit add of the zero-extended high half costs two register moves more).
 __device__ __forceinline__ u64 barrett_lazy_bigq(u64 x, const Mod& m) {
-  unsigned x0, x1, t0, t1;
+  unsigned x0, x1, s0, s1, t0, t1, Q, dummy;
   split(x, x0, x1);
   const unsigned mu0 = lo32(m.mu);
-  const u64 s = mad_wide(hi32(mul_wide(x0, mu0)), 1u, mul_wide(x1, mu0));  // floor(x*mu / 2^32)
-  const unsigned Q = hi32(s);
+  split(mul_wide(x1, mu0), s0, s1);
+  const unsigned h = hi32(mul_wide(x0, mu0));
+  asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, %4, 0;" : "=r"(dummy), "=r"(Q) : "r"(s0), "r"(h), "r"(s1));
+  split(mad_wide(Q, m.n0, x), t0, t1);
+  return join(t0, mad_lo(Q, m.n1, t1));
+}
+// any 64-bit value -> [0,3q) for q >= 2^32 with one wide product less: Q = hi32(x1*mu) is floor(x*mu/2^64) or
+// up to two less.  Enough wherever the result only has to drop below a lazy bound (FAST inverse fix-ups).
+__device__ __forceinline__ u64 barrett_lazy3_bigq(u64 x, const Mod& m) {
+  unsigned x0, x1, t0, t1;
+  split(x, x0, x1);
+  const unsigned Q = hi32(mul_wide(x1, lo32(m.mu)));
   split(mad_wide(Q, m.n0, x), t0, t1);
   return join(t0, mad_lo(Q, m.n1, t1));
 }
@@ -414,7 +427,7 @@ __device__ __forceinline__ typename Ar<MODE>::E stage_cq(int step, const Mod& m)
 template <int K, int NSLOTS, int E = 0>
 __device__ __forceinline__ void inv_pass_fixup(u64* v, const Mod& m) {
   if constexpr (E < NSLOTS) {
-    if constexpr (inv_slot_bound(K, E & ((1 << K) - 1)) > kFastBound) v[E] = barrett_lazy_bigq(v[E], m);
+    if constexpr (inv_slot_bound(K, E & ((1 << K) - 1)) > kFastBound) v[E] = barrett_lazy3_bigq(v[E], m);  // < 3q <= 8q
     inv_pass_fixup<K, NSLOTS, E + 1>(v, m);
   }
 }

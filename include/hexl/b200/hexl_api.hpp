@@ -552,5 +552,41 @@ inline void KeySwitch(uint64_t* result, const uint64_t* t_target_iter_ptr, uint6
                                           modswitch_factors, stream));
 }
 
+// extension: key-switch keys resident on the GPU(s).  The reference reads the keys from caller memory on every
+// call (key-switch.hpp:34-39); a host caller uploads them once here and then switches any number of
+// ciphertexts (`batch` of them back to back per call) without the keys crossing PCIe again.
+namespace b200 {
+class KeySwitchKeys {
+ public:
+  KeySwitchKeys() = default;
+  KeySwitchKeys(const uint64_t** k_switch_keys, uint64_t n, uint64_t decomp_modulus_size, uint64_t key_modulus_size,
+                uint64_t key_component_count) {
+    b200_detail::Throw(hexl_b200_keys_upload(&m_keys, k_switch_keys, n, decomp_modulus_size, key_modulus_size,
+                                             key_component_count));
+  }
+  ~KeySwitchKeys() { hexl_b200_keys_release(m_keys); }
+  KeySwitchKeys(KeySwitchKeys&& o) noexcept : m_keys(o.m_keys) { o.m_keys = nullptr; }
+  KeySwitchKeys& operator=(KeySwitchKeys&& o) noexcept {
+    std::swap(m_keys, o.m_keys);
+    return *this;
+  }
+  KeySwitchKeys(const KeySwitchKeys&) = delete;
+  KeySwitchKeys& operator=(const KeySwitchKeys&) = delete;
+  const hexl_b200_keys* Handle() const { return m_keys; }
+
+ private:
+  hexl_b200_keys* m_keys = nullptr;
+};
+}  // namespace b200
+
+inline void KeySwitch(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n, uint64_t decomp_modulus_size,
+                      uint64_t key_modulus_size, uint64_t rns_modulus_size, uint64_t key_component_count,
+                      const uint64_t* moduli, const b200::KeySwitchKeys& keys, const uint64_t* modswitch_factors,
+                      uint64_t batch = 1, void* stream = nullptr) {
+  b200_detail::Throw(hexl_b200_key_switch_resident(result, t_target_iter_ptr, n, decomp_modulus_size, key_modulus_size,
+                                                   rns_modulus_size, key_component_count, moduli, keys.Handle(),
+                                                   modswitch_factors, batch, stream));
+}
+
 }  // namespace hexl
 }  // namespace intel

@@ -225,6 +225,23 @@ int hexl_b200_key_switch(uint64_t* result, const uint64_t* t_target_iter_ptr, ui
                          const uint64_t* const* k_switch_keys, const uint64_t* modswitch_factors,
                          void* stream);
 
+/* Key-switch keys resident on the GPU.  The reference keeps the keys in caller memory and reads them on every
+ * call (key-switch.hpp:34-39); a host caller of hexl_b200_key_switch therefore pays decomp x key_component_count
+ * x key_modulus_size x n words of PCIe traffic per call.  hexl_b200_keys_upload copies the `decomp` key buffers
+ * (host or device pointers, the layout KeySwitch takes) once to the current device -- to every device listed with
+ * hexl_b200_set_host_devices when that was called -- and hexl_b200_key_switch_resident runs `batch` key switches
+ * against them: ciphertext c uses result + c * key_component_count * decomp * n and t_target + c * decomp * n.
+ * Host buffers are pipelined (copies of one ciphertext under the kernels of its neighbours) and split across the
+ * devices holding the keys; device buffers run on `stream` on their own device. */
+typedef struct hexl_b200_keys hexl_b200_keys;
+int hexl_b200_keys_upload(hexl_b200_keys** out, const uint64_t* const* k_switch_keys, uint64_t n,
+                          uint64_t decomp_modulus_size, uint64_t key_modulus_size, uint64_t key_component_count);
+void hexl_b200_keys_release(hexl_b200_keys* keys);
+int hexl_b200_key_switch_resident(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n,
+                                  uint64_t decomp_modulus_size, uint64_t key_modulus_size, uint64_t rns_modulus_size,
+                                  uint64_t key_component_count, const uint64_t* moduli, const hexl_b200_keys* keys,
+                                  const uint64_t* modswitch_factors, uint64_t batch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

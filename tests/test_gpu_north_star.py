@@ -176,3 +176,109 @@ def test_set_host_devices_across_gpus(hb, checker):
         t.ComputeForward(d, d, 1, 1)
         torch.cuda.synchronize()
     assert (host(d) == checker.ntt_forward(x, n, q)).all()
+
+
+# ------------------------------------- composite host paths: chunked, multi-stream staging and resident keys
+def test_composite_host_paths_span_many_staging_chunks(hb, checker):
+    """Host-pointer RNS calls larger than one 32 MiB staging chunk, with chunk boundaries inside a modulus:
+    forward/inverse multi-modulus transforms, the element-wise RNS ops, the product pipeline and DyadicMultiply."""
+    n, group = 1 << 14, 96                       # 12 MiB per modulus: a 32 MiB chunk ends inside modulus 2
+    mods = [hb.GeneratePrimes(1, b, True, n)[0] for b in (50, 55, 29, 60, 45)]
+    ntts = [hb.NTT(n, q) for q in mods]
+    sz = n * group
+    a = np.concatenate([uniform_below(11 * i + 1, sz, q) for i, q in enumerate(mods)])
+    b = np.concatenate([uniform_below(11 * i + 2, sz, q) for i, q in enumerate(mods)])
+    exp_f = np.concatenate([checker.ntt_forward(a[i * sz:(i + 1) * sz], n, q) for i, q in enumerate(mods)])
+    h = np.zeros_like(a)
+    hb.ComputeForwardMulti(ntts, h, a, 1, 1, batch_per_modulus=group)
+    assert (h == exp_f).all()
+    hb.ComputeInverseMulti(ntts, h, h, 1, 1, batch_per_modulus=group)       # in place
+    assert (h == a).all()
+    prod = np.concatenate([checker.mult_mod(a[i * sz:(i + 1) * sz], b[i * sz:(i + 1) * sz], q) for i, q in enumerate(mods)])
+    hb.EltwiseMultModMulti(h, a, b, sz, mods)
+    assert (h == prod).all()
+    for fn, ref in ((hb.EltwiseAddModMulti, checker.add_mod), (hb.EltwiseSubModMulti, checker.sub_mod)):
+        exp = np.concatenate([ref(a[i * sz:(i + 1) * sz], b[i * sz:(i + 1) * sz], q) for i, q in enumerate(mods)])
+        fn(h, a, b, sz, mods)
+        assert (h == exp).all()
+    fast = [q for q in mods if q < (1 << 61)]
+    conv = np.concatenate([
+        checker.ntt_inverse(checker.mult_mod(checker.ntt_forward(a[i * sz:(i + 1) * sz], n, q),
+                                             checker.ntt_forward(b[i * sz:(i + 1) * sz], n, q), q), n, q)
+        for i, q in enumerate(fast)])
+    k = len(fast) * sz
+    aa, bb = a[:k].copy(), b[:k].copy()
+    hb.PolyMultiplyMulti(ntts[:len(fast)], h[:k], aa, bb, group)
+    assert (h[:k] == conv).all() and (aa == a[:k]).all() and (bb == b[:k]).all()
+    hb.PolyMultiplyMulti(ntts[:len(fast)], bb, aa, bb, group)                  # result aliases b
+    assert (bb == conv).all()
+    # DyadicMultiply: 70 moduli (more than one parameter block and several staging rounds)
+    dn = 1 << 13
+    dm = hb.GeneratePrimes(70, 50, True, dn)
+    x = np.concatenate([uniform_below(10 + i, dn, q) for _ in range(2) for i, q in enumerate(dm)])
+    y = np.concatenate([uniform_below(300 + i, dn, q) for _ in range(2) for i, q in enumerate(dm)])
+    out = np.zeros(3 * dn * len(dm), dtype=np.uint64)
+    hb.DyadicMultiply(out, x, y, dn, dm)
+    assert (out == checker.dyadic_multiply(x, y, dn, dm)).all()
+
+
+def test_key_switch_resident_keys_and_batches(hb, checker):
+    """hexl_b200_keys_upload + hexl_b200_key_switch_resident: several ciphertexts per call against keys uploaded
+    once, host buffers (pipelined over the staging streams) and device buffers, against the reference per ciphertext."""
+    n, decomp, batch = 1 << 13, 7, 5
+    kms, rns, kcc, mods, _, keys, _, modswitch = _c5_case(hb, n, decomp, 50)
+    t_all = np.concatenate([np.concatenate([uniform_below(900 * c + j, n, mods[j]) for j in range(decomp)])
+                            for c in range(batch)])
+    r_all = np.concatenate([np.concatenate([uniform_below(7000 * c + 10 * k + i, n, mods[i]) for k in range(kcc)
+                                            for i in range(decomp)]) for c in range(batch)])
+    res_sz, t_sz = kcc * decomp * n, decomp * n
+    exp = np.concatenate([checker.key_switch(r_all[c * res_sz:(c + 1) * res_sz].copy(), t_all[c * t_sz:(c + 1) * t_sz], n,
+                                             decomp, kms, rns, kcc, mods, keys, modswitch) for c in range(batch)])
+    handle = hb.KeySwitchKeys(keys, n, decomp, kms, kcc)                       # from host buffers
+    got = r_all.copy()
+    hb.KeySwitchResident(got, t_all, n, decomp, kms, rns, kcc, mods, handle, modswitch, batch)
+    assert (got == exp).all()
+    d = dev(r_all)
+    hb.KeySwitchResident(d, dev(t_all), n, decomp, kms, rns, kcc, mods, handle, modswitch, batch)
+    assert (host(d) == exp).all()
+    handle2 = hb.KeySwitchKeys([dev(k) for k in keys], n, decomp, kms, kcc)    # from device buffers
+    got = r_all[:res_sz].copy()
+    hb.KeySwitchResident(got, t_all[:t_sz], n, decomp, kms, rns, kcc, mods, handle2, modswitch)
+    assert (got == exp[:res_sz]).all()
+    with pytest.raises(hb.HexlB200Error):                                     # shape mismatch is refused
+        hb.KeySwitchResident(got, t_all[:t_sz], n // 2, decomp, kms, rns, kcc, mods, handle2, modswitch)
+    ndev = hb.device_count()
+    if ndev >= 2:                                                             # keys on every device, batch split
+        try:
+            hb.set_host_devices(list(range(ndev)))
+            h3 = hb.KeySwitchKeys(keys, n, decomp, kms, kcc)
+            got = r_all.copy()
+            hb.KeySwitchResident(got, t_all, n, decomp, kms, rns, kcc, mods, h3, modswitch, batch)
+            assert (got == exp).all()
+        finally:
+            hb.set_host_devices([])
+
+
+def test_cold_handle_inside_a_capture_is_refused_and_prepare_fixes_it(hb, checker):
+    """The first transform of a handle on a device uploads its tables synchronously, which a stream capture
+    forbids: the call reports that instead of killing the capture; NTT.Prepare() warms the handle."""
+    n = 1 << 11
+    q = hb.GeneratePrimes(1, 47, True, n)[0]
+    x = uniform_below(4, n, q)
+    d, o = dev(x), dev(np.zeros_like(x))
+    cold = hb.NTT(n, q)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        g = torch.cuda.CUDAGraph()
+        g.capture_begin()
+        with pytest.raises(hb.HexlB200Error):
+            cold.ComputeForward(o, d, 1, 1)
+        cold_ok = hb.NTT(n, q)
+        g.capture_end()
+    warm = hb.NTT(n, q).Prepare()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        warm.ComputeForward(o, d, 1, 1)
+    g2.replay()
+    torch.cuda.synchronize()
+    assert (host(o) == checker.ntt_forward(x, n, q)).all()

@@ -105,6 +105,37 @@ __device__ __forceinline__ void bf5(u64& X, u64& Y, Tw w, const Mod& m) {
   u64 T = mad_chain5(Y, w.w, mulhi_approx5(Y, w.wp), m);
   Y = X + m.four_q - T; X = X + T;
 }
+// ---- variant 12/13: the quotient sum as plain 64-bit adds of zero-extended high halves (IADD3 with two carry-outs
+//   + IADD3.X) instead of multiply-by-one wide mads (which ptxas turns into register-pair moves plus adds)
+__device__ __forceinline__ void bf12(u64& X, u64& Y, Tw w, const Mod& m) {
+  unsigned a0, a1, b0, b1; split(Y, a0, a1); split(w.wp, b0, b1);
+  const u64 Q = mulwide(a1, b1) + (u64)hi32(mulwide(a1, b0)) + (u64)hi32(mulwide(a0, b1));
+  u64 T = mad_chain5(Y, w.w, Q, m);
+  Y = X + m.four_q - T; X = X + T;
+}
+__device__ __forceinline__ void bf13(u64& X, u64& Y, Tw w, const Mod& m) {
+  unsigned a0, a1, b0, b1; split(Y, a0, a1); split(w.wp, b0, b1);
+  const u64 Q = mulwide(a1, b1) + (u64)__umulhi(a1, b0) + (u64)__umulhi(a0, b1);
+  u64 T = mad_chain5(Y, w.w, Q, m);
+  Y = X + m.four_q - T; X = X + T;
+}
+// ---- variant 14: the two high halves are summed first (one 64-bit add) and ride in as the accumulator of a1*b1
+__device__ __forceinline__ void bf14(u64& X, u64& Y, Tw w, const Mod& m) {
+  unsigned a0, a1, b0, b1; split(Y, a0, a1); split(w.wp, b0, b1);
+  const u64 hs = (u64)hi32(mulwide(a1, b0)) + (u64)hi32(mulwide(a0, b1));
+  const u64 Q = madwide(a1, b1, hs);
+  u64 T = mad_chain5(Y, w.w, Q, m);
+  Y = X + m.four_q - T; X = X + T;
+}
+// ---- variant 15: same with explicit carry instructions
+__device__ __forceinline__ void bf15(u64& X, u64& Y, Tw w, const Mod& m) {
+  unsigned a0, a1, b0, b1; split(Y, a0, a1); split(w.wp, b0, b1);
+  unsigned h1 = hi32(mulwide(a1, b0)), h2 = hi32(mulwide(a0, b1)), s0, s1;
+  asm("add.cc.u32 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=r"(s0), "=r"(s1) : "r"(h1), "r"(h2));
+  const u64 Q = madwide(a1, b1, join2(s0, s1));
+  u64 T = mad_chain5(Y, w.w, Q, m);
+  Y = X + m.four_q - T; X = X + T;
+}
 // ---- variant 6: exact mulhi (compiler's __umul64hi) + pinned mad chain, no csub (FAST-exact)
 __device__ __forceinline__ void bf6(u64& X, u64& Y, Tw w, const Mod& m) {
   u64 T = mad_chain5(Y, w.w, __umul64hi(Y, w.wp), m);
@@ -229,6 +260,8 @@ template <int MINB, int VAR = 10> void run10(const char* name, u64* out, const T
 
 template <int V> __device__ __forceinline__ void bf(u64& X, u64& Y, Tw w, const Mod& m) {
   if (V == 5) { bf5(X, Y, w, m); return; } if (V == 6) { bf6(X, Y, w, m); return; }
+  if (V == 14) { bf14(X, Y, w, m); return; } if (V == 15) { bf15(X, Y, w, m); return; }
+  if (V == 12) { bf12(X, Y, w, m); return; } if (V == 13) { bf13(X, Y, w, m); return; }
   if (V == 7) { bf7(X, Y, w, m); return; } if (V == 8) { bf8(X, Y, w, m); return; }
   if (V == 0) bf0(X, Y, w, m); else if (V == 1) bf1(X, Y, w, m); else if (V == 2) bf2(X, Y, w, m);
   else if (V == 3) bf3(X, Y, w, m); else bf4(X, Y, w, m);
@@ -357,6 +390,14 @@ int main() {
   run10<2, 11>("v11 fp64 I2F 2xDFMA", out, tw, m, 3);
   run10<3, 11>("v11 mb3", out, tw, m, 3);
   run10<3, 11>("v11 mb3 x4", out, tw, m, 4);
+  run<12, 2>("v12 plain 64-bit quotient adds", out, tw, m, 2);
+  run<12, 3>("v12 mb3", out, tw, m, 3);
+  run<14, 2>("v14 hs as accumulator", out, tw, m, 2);
+  run<14, 3>("v14 mb3", out, tw, m, 3);
+  run<15, 2>("v15 hs via add.cc", out, tw, m, 2);
+  run<15, 3>("v15 mb3", out, tw, m, 3);
+  run<13, 2>("v13 IMAD.HI + plain adds", out, tw, m, 2);
+  run<13, 3>("v13 mb3", out, tw, m, 3);
   run<5, 3>("v5 mb3", out, tw, m, 3);
   run<6, 3>("v6 mb3", out, tw, m, 3);
   run<7, 3>("v7 mb3", out, tw, m, 3);
