@@ -113,6 +113,11 @@ _sig("hexl_b200_ntt_get_cached", _int, [C.POINTER(_vp), _u64, _u64])
 _sig("hexl_b200_dyadic_multiply", _int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp])
 _sig("hexl_b200_key_switch", _int, [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp, _vp, _vp])
 
+_sig("hexl_b200_hensel_lemma_2adic_root", _u64, [C.c_uint32, _u64])
+_sig("hexl_b200_montgomery_reduce", _u64, [_u64, _u64, _u64, _int, _u64])
+_sig("hexl_b200_eltwise_mont_reduce_mod", _int, [_vp, _vp, _vp, _u64, _u64, _int, _u64, _vp])
+_sig("hexl_b200_eltwise_montgomery_form_in", _int, [_vp, _vp, _u64, _u64, _u64, _int, _u64, _vp])
+_sig("hexl_b200_eltwise_montgomery_form_out", _int, [_vp, _vp, _u64, _u64, _int, _u64, _vp])
 _sig("hexl_b200_keys_upload", _int, [C.POINTER(_vp), _vp, _u64, _u64, _u64, _u64])
 _sig("hexl_b200_keys_release", None, [_vp])
 _sig("hexl_b200_key_switch_resident", _int, [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp, _vp, _u64, _vp])
@@ -421,6 +426,33 @@ def EltwiseCmpSubMod(result, operand1, n, modulus, cmp, bound, diff, stream=None
     _need("result", rn, n); _need("operand1", an, n)
     _check(_lib.hexl_b200_eltwise_cmp_sub_mod(rp, ap, n, modulus, int(cmp), bound, diff,
                                               _stream(stream, rc or ac)))
+    return result
+
+
+# ------------------------------------------------------- Montgomery-form helpers
+def HenselLemma2adicRoot(r, q): return int(_lib.hexl_b200_hensel_lemma_2adic_root(r, q))
+def MontgomeryReduce(T_hi, T_lo, q, r, inv_mod): return int(_lib.hexl_b200_montgomery_reduce(T_hi, T_lo, q, r, inv_mod))
+
+
+def EltwiseMontReduceMod(result, a, b, n, modulus, r, neg_inv_mod, stream=None):
+    """a*b*R^-1 mod q, R = 2^r (EltwiseMontReduceModAVX512<64, r>, eltwise-reduce-mod-avx512.hpp:156)"""
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(a); bp, bn, _ = _buf(b)
+    _need("result", rn, n); _need("a", an, n); _need("b", bn, n)
+    _check(_lib.hexl_b200_eltwise_mont_reduce_mod(rp, ap, bp, n, modulus, r, neg_inv_mod, _stream(stream, rc or ac)))
+    return result
+
+
+def EltwiseMontgomeryFormIn(result, a, R2_mod_q, n, modulus, r, neg_inv_mod, stream=None):
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(a)
+    _need("result", rn, n); _need("a", an, n)
+    _check(_lib.hexl_b200_eltwise_montgomery_form_in(rp, ap, R2_mod_q, n, modulus, r, neg_inv_mod, _stream(stream, rc or ac)))
+    return result
+
+
+def EltwiseMontgomeryFormOut(result, a, n, modulus, r, neg_inv_mod, stream=None):
+    rp, rn, rc = _buf(result); ap, an, ac = _buf(a)
+    _need("result", rn, n); _need("a", an, n)
+    _check(_lib.hexl_b200_eltwise_montgomery_form_out(rp, ap, n, modulus, r, neg_inv_mod, _stream(stream, rc or ac)))
     return result
 
 

@@ -606,6 +606,19 @@ int scratch_pool(cudaMemPool_t* out) {
   return 0;
 }
 
+}  // namespace
+namespace hexl_b200 {
+cudaError_t scratch_alloc_async(void** p, size_t bytes, cudaStream_t stream) {
+  cudaMemPool_t pool;
+  if (scratch_pool(&pool)) return cudaErrorMemoryAllocation;
+  return cudaMallocFromPoolAsync(p, bytes, pool, stream);
+}
+void scratch_free_async(void* p, cudaStream_t stream) {
+  if (p) cudaFreeAsync(p, stream);
+}
+}  // namespace hexl_b200
+namespace {
+
 struct Scratch {
   cudaStream_t s;
   std::vector<void*> ptrs;
@@ -1189,6 +1202,46 @@ int hexl_b200_eltwise_cmp_sub_mod(uint64_t* result, const uint64_t* op1, uint64_
   p.result = result; p.a = op1; p.n = n; p.q = q; p.scalar = bound; p.scalar_p = diff; p.cmp = cmp;
   p.mu = nt::multiply_factor(1, 64, q);
   return eltwise_dispatch(EltOp::CmpSubMod, p, stream);
+}
+
+// ---- Montgomery-form helpers
+uint64_t hexl_b200_hensel_lemma_2adic_root(uint32_t r, uint64_t q) {
+  if (r == 0 || r > 64 || !(q & 1)) return 0;
+  return nt::neg_inverse_mod_pow2(r, q);
+}
+uint64_t hexl_b200_montgomery_reduce(uint64_t T_hi, uint64_t T_lo, uint64_t q, int r, uint64_t inv_mod) {
+  if (r < 1 || r > 62 || q < 2) return 0;
+  return nt::montgomery_reduce(T_hi, T_lo, q, r, inv_mod);
+}
+static int mont_dispatch(EltOp op, uint64_t* result, const uint64_t* a, const uint64_t* b, uint64_t scalar, uint64_t n,
+                         uint64_t q, int r, uint64_t neg_inv_mod, void* stream) {
+  // checks of eltwise-reduce-mod-avx512.hpp:160-176
+  REQUIRE(result && a && (op != EltOp::MontMult || b), "Require result, operands != nullptr");
+  REQUIRE(n != 0, "Require n != 0");
+  REQUIRE(q > 1, "Require modulus > 1");
+  REQUIRE(q & 1, "gcd(modulus, R) != 1");
+  REQUIRE(r >= 1 && r <= 62, "With r > 62 internal ops might overflow");
+  REQUIRE((1ull << r) > q, "Needs R bigger than q.");
+  REQUIRE(((q * neg_inv_mod + 1) & ((1ull << r) - 1)) == 0, "neg_inv_mod is not -1/q mod R");
+  if (int rc = debug_bounds(a, n, q, "operand a", {result, a, b})) return rc;
+  if (op == EltOp::MontMult)
+    if (int rc = debug_bounds(b, n, q, "operand b", {result, a, b})) return rc;
+  EltParams p{};
+  p.result = result; p.a = a; p.b = b; p.n = n; p.q = q; p.mu = neg_inv_mod & ((1ull << r) - 1); p.shift = r; p.scalar = scalar;
+  return eltwise_dispatch(op, p, stream);
+}
+int hexl_b200_eltwise_mont_reduce_mod(uint64_t* result, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t q,
+                                      int r, uint64_t neg_inv_mod, void* stream) {
+  return mont_dispatch(EltOp::MontMult, result, a, b, 0, n, q, r, neg_inv_mod, stream);
+}
+int hexl_b200_eltwise_montgomery_form_in(uint64_t* result, const uint64_t* a, uint64_t R2_mod_q, uint64_t n, uint64_t q,
+                                         int r, uint64_t neg_inv_mod, void* stream) {
+  REQUIRE(R2_mod_q < q, "Require R2_mod_q < modulus");
+  return mont_dispatch(EltOp::MontIn, result, a, nullptr, R2_mod_q, n, q, r, neg_inv_mod, stream);
+}
+int hexl_b200_eltwise_montgomery_form_out(uint64_t* result, const uint64_t* a, uint64_t n, uint64_t q, int r,
+                                          uint64_t neg_inv_mod, void* stream) {
+  return mont_dispatch(EltOp::MontOut, result, a, nullptr, 0, n, q, r, neg_inv_mod, stream);
 }
 
 // ---- SEAL-shaped composites

@@ -13,6 +13,7 @@
 //   ReduceMod   hexl/eltwise/eltwise-reduce-mod.cpp:16-79,94-99
 //   CmpAdd      hexl/eltwise/eltwise-cmp-add.cpp:32-106
 //   CmpSubMod   hexl/eltwise/eltwise-cmp-sub-mod.cpp:47-66
+//   Montgomery  hexl/include/hexl/number-theory/number-theory.hpp:269-301; hexl/eltwise/eltwise-reduce-mod-avx512.hpp:156-352
 #include "internal.h"
 
 namespace hexl_b200 {
@@ -118,6 +119,36 @@ struct FCmpSubMod {
     r = r >= q ? r - q : r;
     return hit ? (r >= diff ? r - diff : r + q - diff) : r;
   }
+};
+
+// Montgomery reduction with R = 2^r, q < R <= 2^62 (MontgomeryReduce<64>, number-theory.hpp:269-301; the element-wise
+// helpers of hexl/eltwise/eltwise-reduce-mod-avx512.hpp:156-352): T = hi:lo < q*R -> T / R mod q in [0, q).
+// (T + m q) is a multiple of R below 2 q R <= 2^125; its quotient by R is assembled from the two 64-bit halves.
+struct MontParams {
+  u64 q, ninv;  // ninv = -q^-1 mod R
+  int r;
+  __device__ __forceinline__ u64 redc(u64 hi, u64 lo) const {
+    const u64 mask = (1ull << r) - 1;
+    const u64 mm = ((lo & mask) * ninv) & mask;
+    const u64 mq_lo = mm * q, mq_hi = mulhi(mm, q);
+    const u64 t_lo = lo + mq_lo;
+    const u64 t_hi = hi + mq_hi + (t_lo < lo ? 1ull : 0ull);
+    const u64 s = (t_hi << (64 - r)) | (t_lo >> r);
+    return csub(s, q);
+  }
+};
+struct FMontMult {
+  MontParams p;
+  __device__ __forceinline__ u64 operator()(u64 a, u64 b) const { return p.redc(mulhi(a, b), a * b); }
+};
+struct FMontIn {
+  MontParams p;
+  u64 r2;  // R^2 mod q
+  __device__ __forceinline__ u64 operator()(u64 a, u64) const { return p.redc(mulhi(a, r2), a * r2); }
+};
+struct FMontOut {
+  MontParams p;
+  __device__ __forceinline__ u64 operator()(u64 a, u64) const { return p.redc(0, a); }
 };
 
 // NIN = number of vector inputs.  VEC = 2 -> 128-bit accesses (n counts pairs).
@@ -228,6 +259,9 @@ cudaError_t launch_eltwise(EltOp op, const EltParams& p, cudaStream_t s) {
       return p.out_mf == 1 ? run<FReduce<4, 1>, 1>(p, FReduce<4, 1>{p.q, p.mu}, s)
                            : run<FReduce<4, 2>, 1>(p, FReduce<4, 2>{p.q, p.mu}, s);
     case EltOp::Copy: return run<FCopy, 1>(p, FCopy{}, s);
+    case EltOp::MontMult: return run<FMontMult, 2>(p, FMontMult{MontParams{p.q, p.mu, p.shift}}, s);
+    case EltOp::MontIn: return run<FMontIn, 1>(p, FMontIn{MontParams{p.q, p.mu, p.shift}, p.scalar}, s);
+    case EltOp::MontOut: return run<FMontOut, 1>(p, FMontOut{MontParams{p.q, p.mu, p.shift}}, s);
     case EltOp::CmpAdd: return run<FCmpAdd, 1>(p, FCmpAdd{p.scalar, p.scalar_p, p.cmp}, s);
     case EltOp::CmpSubMod:
       return run<FCmpSubMod, 1>(p, FCmpSubMod{p.q, p.mu, p.scalar, p.scalar_p, p.cmp}, s);

@@ -9,7 +9,8 @@ namespace hexl_b200 {
 
 // ------------------------------------------------------------------ eltwise
 enum class EltOp : int {
-  AddVV, AddVS, SubVV, SubVS, MultVV, Fma, FmaNoAdd, Reduce, Copy, CmpAdd, CmpSubMod
+  AddVV, AddVS, SubVV, SubVS, MultVV, Fma, FmaNoAdd, Reduce, Copy, CmpAdd, CmpSubMod,
+  MontMult, MontIn, MontOut  // Montgomery form, R = 2^shift: a*b/R, a*scalar/R (scalar = R^2 mod q), a/R; mu = -q^-1 mod R
 };
 
 struct EltParams {
@@ -124,6 +125,10 @@ cudaError_t launch_ks_round(u64* tmp, const u64* t_last, u64 n, u64 kcc, u64 q_l
 // result[k][i0+e][l] = (result + (prod[e][k][l] + 4 q_e - tmp[e][k][l]) * a_e) mod q_e ; result has `decomp` moduli per k
 cudaError_t launch_ks_finish(u64* result, const u64* prod, const u64* tmp, u64 n, u64 kcc, u64 decomp, u64 i0,
                              u64 count, const KsModuli& mods, cudaStream_t stream);
+
+// Stream-ordered scratch from the library's own memory pool (capi.cu): kept warm between calls, capturable.
+cudaError_t scratch_alloc_async(void** p, size_t bytes, cudaStream_t stream);
+void scratch_free_async(void* p, cudaStream_t stream);
 
 // launches issued so far (all kernels of this library)
 void count_launch(unsigned n = 1);

@@ -1,4 +1,6 @@
 // Single-modulus NTT launchers (the kernels are in ntt_kernels.cuh).
+#include <algorithm>
+
 #include "ntt_kernels.cuh"
 
 namespace hexl_b200 {
@@ -122,6 +124,66 @@ cudaError_t launch_fused(bool fwd, const NttDeviceTables& t, u64* result, const 
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// The persistent pipelined kernel: one launch, work items from a global counter (ntt_kernels.cuh).
+// HEXL_B200_PIPE: 1 = use it for N = 2^14 .. 2^17 (default), 0 = off; HEXL_B200_PIPE_LOOKAHEAD = polynomials
+// between a producer block and its consumers (default 16), HEXL_B200_PIPE_CTAS = CTAs per SM (default: the
+// kernel's launch bound).
+template <int MODE, int LOGR>
+cudaError_t launch_pipe(bool fwd, const NttDeviceTables& t, u64* result, const u64* operand, u64 batch, int out_mf,
+                        cudaStream_t stream) {
+  using Cfg = PipeCfg<LOGR, MODE>;
+  static const int lookahead_env = env_int("HEXL_B200_PIPE_LOOKAHEAD", 16);
+  static const int ctas_env = env_int("HEXL_B200_PIPE_CTAS", 0);
+  const Mod m = make_mod(t);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned lookahead = (unsigned)std::max(1, lookahead_env);
+  const u64 items = (batch + lookahead) * Cfg::SLOTS;
+  const int per_sm = ctas_env > 0 ? ctas_env : Cfg::MIN_BLOCKS;
+  const unsigned grid = (unsigned)std::min<u64>((u64)sms * per_sm, items);
+  unsigned* state = nullptr;  // [0] = work counter, [1 + p] = producers of polynomial p that have finished
+  const size_t bytes = (size_t)(batch + 1) * sizeof(unsigned);
+  cudaError_t e = scratch_alloc_async(reinterpret_cast<void**>(&state), bytes, stream);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(state, 0, bytes, stream)) != cudaSuccess) return e;
+  if (fwd) {
+    if ((e = ensure_dynamic_smem<ntt_pipe_fwd<MODE, LOGR>>(Cfg::SMEM)) != cudaSuccess) return e;
+    ntt_pipe_fwd<MODE, LOGR><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, Tab<MODE>::fwd(t), m, out_mf,
+                                                                        (unsigned)batch, lookahead, state, state + 1);
+  } else {
+    if ((e = ensure_dynamic_smem<ntt_pipe_inv<MODE, LOGR>>(Cfg::SMEM)) != cudaSuccess) return e;
+    ntt_pipe_inv<MODE, LOGR><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, Tab<MODE>::inv(t), m, out_mf,
+                                                                        Tab<MODE>::inv_n(t), Tab<MODE>::inv_n_w(t),
+                                                                        (unsigned)batch, lookahead, state, state + 1);
+  }
+  count_launch();
+  e = cudaGetLastError();
+  scratch_free_async(state, stream);
+  return e;
+}
+
+template <int MODE>
+cudaError_t launch_pipe_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64* result, const u64* operand, u64 batch,
+                            int out_mf, cudaStream_t stream) {
+  switch (log_r) {
+    case 2: return launch_pipe<MODE, 2>(fwd, t, result, operand, batch, out_mf, stream);
+    case 3: return launch_pipe<MODE, 3>(fwd, t, result, operand, batch, out_mf, stream);
+    case 4: return launch_pipe<MODE, 4>(fwd, t, result, operand, batch, out_mf, stream);
+    case 5: return launch_pipe<MODE, 5>(fwd, t, result, operand, batch, out_mf, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// log2(N / 4096) for which the pipelined kernel is used; 0 = none.  A batch of fewer polynomials than the
+// pipeline is deep gains nothing from it.
+inline int pipe_log_r(int log_n, u64 batch) {
+  static const int mode = env_int("HEXL_B200_PIPE", 0);
+  static const int min_batch = env_int("HEXL_B200_PIPE_MIN_BATCH", 64);
+  const int lr = log_n - 12;
+  return (mode != 0 && lr >= 2 && lr <= 5 && batch >= (u64)min_batch && batch < (1ull << 31)) ? lr : 0;
+}
+
 // SMALL mode: the single kernel that keeps the intermediate in the cluster's shared memory
 template <int LOGR>
 cudaError_t launch_dsmem(bool fwd, const NttDeviceTables& t, u64* result, const u64* operand, u64 batch, int out_mf,
@@ -197,6 +259,7 @@ cudaError_t launch_fused_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64*
 template <int MODE>
 cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
+  if (const int lr = pipe_log_r(t.log_n, batch)) return launch_pipe_dyn<MODE>(lr, true, t, result, operand, batch, out_mf, stream);
   if constexpr (MODE == kSmall)
     if (const int lr = dsmem_log_r(t.log_n)) return launch_dsmem_dyn(lr, true, t, result, operand, batch, out_mf, stream);
   if (const int lr = fused_log_r<MODE>(t.log_n)) return launch_fused_dyn<MODE>(lr, true, t, result, operand, batch, out_mf, stream);
@@ -217,6 +280,7 @@ cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* opera
 template <int MODE>
 cudaError_t inverse_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
+  if (const int lr = pipe_log_r(t.log_n, batch)) return launch_pipe_dyn<MODE>(lr, false, t, result, operand, batch, out_mf, stream);
   if constexpr (MODE == kSmall)
     if (const int lr = dsmem_log_r(t.log_n)) return launch_dsmem_dyn(lr, false, t, result, operand, batch, out_mf, stream);
   if (const int lr = fused_log_r<MODE>(t.log_n)) return launch_fused_dyn<MODE>(lr, false, t, result, operand, batch, out_mf, stream);

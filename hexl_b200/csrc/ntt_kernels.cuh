@@ -930,6 +930,121 @@ __global__ void __launch_bounds__(FusedCfg<LOGR, MODE>::THREADS, FusedCfg<LOGR, 
                                                  out_mf, true, inv_n, inv_n_w);
 }
 
+// ------------------------------------------------ persistent pipelined single kernel
+// N = R * 4096 as above, ONE launch per batch, HBM sees each coefficient once in and once out, and no
+// barrier wider than a CTA.  The grid is persistent (a few CTAs per SM) and pulls work items from a
+// global counter.  Items come in the order
+//     block b:  the 16 column tiles of polynomial b,  then the R rows of polynomial b - D
+// (forward; the inverse runs rows of b, then column tiles of b - D).  A column tile is 256 columns of R
+// coefficients (the top log2 R stages in registers); a row is a 4096-point transform.  The consumer of a
+// polynomial waits on a per-polynomial counter its producers bump with release semantics -- but the
+// producers were claimed D*(16+R) items earlier, far more than the number of CTAs in flight, so the wait
+// is normally over before it starts, and since producers never wait the scheme cannot deadlock.  The
+// intermediate is written and read back with .cg accesses: it lives in the 126 MB L2 (D polynomials of
+// 8N bytes) and is overwritten in place by the consumer before L2 has a reason to write it back.
+// Memory-bound column tiles and multiplier-bound rows of DIFFERENT polynomials share every SM at all
+// times, which is what the cluster version above could not do (its two phases are serialised per CTA).
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int LOGR, int MODE = kGeneric>
+struct PipeCfg {
+  static constexpr int LOGC = 12, C = 1 << LOGC, R = 1 << LOGR;
+  static constexpr int THREADS = 256;
+  static constexpr int CT = C / THREADS;             // column tiles per polynomial
+  static constexpr int SLOTS = CT + R;               // work items per block
+  static constexpr int MIN_BLOCKS = FusedCfg<LOGR, MODE>::MIN_BLOCKS;
+  static constexpr size_t SMEM = RowCfg<LOGC, MODE>::ROW_BYTES;
+};
+
+template <int MODE, int LOGR>
+__global__ void __launch_bounds__(PipeCfg<LOGR, MODE>::THREADS, PipeCfg<LOGR, MODE>::MIN_BLOCKS)
+    ntt_pipe_fwd(u64* result, const u64* operand, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod m,
+                 int out_mf, unsigned batch, unsigned lookahead, unsigned* counter, unsigned* done) {
+  using Cfg = PipeCfg<LOGR, MODE>;
+  using E = typename Ar<MODE>::E;
+  using Tw = typename Ar<MODE>::Tw;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  E* smem = reinterpret_cast<E*>(smem_raw);
+  __shared__ Tw stw[Cfg::R];
+  __shared__ unsigned s_item;
+  for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
+    if (l) stw[l] = ld_tw(tw + l);                   // root sub-tree: local node == global node
+  const unsigned total = (batch + lookahead) * Cfg::SLOTS;
+  while (true) {
+    __syncthreads();                                 // s_item and the row buffer are free again
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1u);
+    __syncthreads();
+    const unsigned item = s_item;
+    if (item >= total) break;
+    const unsigned blk = item / Cfg::SLOTS, j = item % Cfg::SLOTS;
+    if (j < (unsigned)Cfg::CT) {                     // column tile j of polynomial blk
+      if (blk >= batch) continue;
+      const u64 poly_off = (u64)blk << (Cfg::LOGC + LOGR);
+      col_body<MODE, LOGR, true, kStream, kViaL2>(result, operand, poly_off + j * Cfg::THREADS + threadIdx.x, Cfg::LOGC,
+                                                  stw, m, out_mf, false, Tw{}, Tw{});
+      __syncthreads();                               // every thread's stores precede the release below
+      if (threadIdx.x == 0) red_release_gpu(done + blk, 1u);
+    } else {                                         // row j - CT of polynomial blk - lookahead
+      if (blk < lookahead) continue;
+      const unsigned p = blk - lookahead, r = j - Cfg::CT;
+      if (threadIdx.x == 0)
+        while (ld_acquire_gpu(done + p) < (unsigned)Cfg::CT) __nanosleep(100);
+      __syncthreads();
+      u64* row = result + ((u64)p << (Cfg::LOGC + LOGR)) + (u64)r * Cfg::C;
+      row_fwd_body<MODE, Cfg::LOGC, kViaL2, kStream>(row, row, smem, threadIdx.x, (u64)Cfg::R + r, tw, m, out_mf, true);
+    }
+  }
+}
+
+template <int MODE, int LOGR>
+__global__ void __launch_bounds__(PipeCfg<LOGR, MODE>::THREADS, PipeCfg<LOGR, MODE>::MIN_BLOCKS)
+    ntt_pipe_inv(u64* result, const u64* operand, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod m,
+                 int out_mf, typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w, unsigned batch,
+                 unsigned lookahead, unsigned* counter, unsigned* done) {
+  using Cfg = PipeCfg<LOGR, MODE>;
+  using E = typename Ar<MODE>::E;
+  using Tw = typename Ar<MODE>::Tw;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  E* smem = reinterpret_cast<E*>(smem_raw);
+  __shared__ Tw stw[Cfg::R];
+  __shared__ unsigned s_item;
+  for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
+    if (l) stw[l] = ld_tw(tw + l);
+  const unsigned total = (batch + lookahead) * Cfg::SLOTS;
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1u);
+    __syncthreads();
+    const unsigned item = s_item;
+    if (item >= total) break;
+    const unsigned blk = item / Cfg::SLOTS, j = item % Cfg::SLOTS;
+    if (j < (unsigned)Cfg::R) {                      // row j of polynomial blk
+      if (blk >= batch) continue;
+      const u64 off = ((u64)blk << (Cfg::LOGC + LOGR)) + (u64)j * Cfg::C;
+      row_inv_body<MODE, Cfg::LOGC, kStream, kViaL2>(result + off, operand + off, smem, threadIdx.x, (u64)Cfg::R + j, tw,
+                                                     m, out_mf, false, inv_n, inv_n_w, true);
+      __syncthreads();
+      if (threadIdx.x == 0) red_release_gpu(done + blk, 1u);
+    } else {                                         // column tile j - R of polynomial blk - lookahead
+      if (blk < lookahead) continue;
+      const unsigned p = blk - lookahead, t = j - Cfg::R;
+      if (threadIdx.x == 0)
+        while (ld_acquire_gpu(done + p) < (unsigned)Cfg::R) __nanosleep(100);
+      __syncthreads();
+      const u64 poly_off = (u64)p << (Cfg::LOGC + LOGR);
+      col_body<MODE, LOGR, false, kViaL2, kStream>(result, result, poly_off + t * Cfg::THREADS + threadIdx.x, Cfg::LOGC,
+                                                   stw, m, out_mf, true, inv_n, inv_n_w);
+    }
+  }
+}
+
 // ------------------------------------- fused kernels through distributed shared memory
 // SMALL mode only (32-bit words): the whole polynomial fits in the shared memory of its
 // cluster -- N * 4 bytes spread over K CTAs -- so the intermediate between the column phase

@@ -140,5 +140,23 @@ std::vector<uint64_t> generate_primes(size_t num, size_t bits, bool prefer_small
   return out;
 }
 
+// HenselLemma2adicRoot of the reference (number-theory.hpp:303-336) lifts one bit per step; the 2-adic Newton
+// iteration x <- x (2 - q x) doubles the number of correct bits per step and lands on the same unique value.
+uint64_t neg_inverse_mod_pow2(uint32_t r, uint64_t q) {
+  uint64_t x = q;                       // q * q = 1 mod 8 for odd q: 3 correct bits
+  for (int i = 0; i < 5; ++i) x *= 2 - q * x;  // 6, 12, 24, 48, 96 bits
+  const uint64_t mask = r >= 64 ? ~0ull : ((1ull << r) - 1);
+  return (0 - x) & mask;
+}
+
+uint64_t montgomery_reduce(uint64_t T_hi, uint64_t T_lo, uint64_t q, int r, uint64_t inv_mod) {
+  typedef unsigned __int128 u128;
+  const uint64_t mask = (1ull << r) - 1;
+  const uint64_t m = ((T_lo & mask) * inv_mod) & mask;
+  const u128 t = (((u128)T_hi << 64) | T_lo) + (u128)m * q;
+  const uint64_t s = (uint64_t)(t >> r);
+  return s >= q ? s - q : s;
+}
+
 }  // namespace nt
 }  // namespace hexl_b200

@@ -528,6 +528,28 @@ inline void EltwiseCmpSubMod(uint64_t* result, const uint64_t* operand1, uint64_
       hexl_b200_eltwise_cmp_sub_mod(result, operand1, n, modulus, static_cast<int>(cmp), bound, diff, stream));
 }
 
+// Montgomery-form helpers.  In the reference these are internal AVX-512 templates on <BitShift, r>
+// (hexl/eltwise/eltwise-reduce-mod-avx512.hpp:156-352); here r is a run-time argument and BitShift is 64.
+inline uint64_t HenselLemma2adicRoot(uint32_t r, uint64_t q) { return hexl_b200_hensel_lemma_2adic_root(r, q); }
+template <int BitShift>
+inline uint64_t MontgomeryReduce(uint64_t T_hi, uint64_t T_lo, uint64_t q, int r, uint64_t /*mod_R_msk*/,
+                                 uint64_t inv_mod) {
+  static_assert(BitShift == 64, "only the 64-bit form exists on the GPU path");
+  return hexl_b200_montgomery_reduce(T_hi, T_lo, q, r, inv_mod);
+}
+inline void EltwiseMontReduceMod(uint64_t* result, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t modulus,
+                                 int r, uint64_t neg_inv_mod, void* stream = nullptr) {
+  b200_detail::Throw(hexl_b200_eltwise_mont_reduce_mod(result, a, b, n, modulus, r, neg_inv_mod, stream));
+}
+inline void EltwiseMontgomeryFormIn(uint64_t* result, const uint64_t* a, uint64_t R2_mod_q, uint64_t n, uint64_t modulus,
+                                    int r, uint64_t neg_inv_mod, void* stream = nullptr) {
+  b200_detail::Throw(hexl_b200_eltwise_montgomery_form_in(result, a, R2_mod_q, n, modulus, r, neg_inv_mod, stream));
+}
+inline void EltwiseMontgomeryFormOut(uint64_t* result, const uint64_t* a, uint64_t n, uint64_t modulus, int r,
+                                     uint64_t neg_inv_mod, void* stream = nullptr) {
+  b200_detail::Throw(hexl_b200_eltwise_montgomery_form_out(result, a, n, modulus, r, neg_inv_mod, stream));
+}
+
 // ------------------------------------------------ SEAL-shaped composites
 // hexl/include/hexl/experimental/seal/ntt-cache.hpp:27-53.  The reference returns
 // NTT& into a process-wide map; here the cache lives behind the ABI and a cheap

@@ -205,6 +205,21 @@ int hexl_b200_eltwise_cmp_sub_mod(uint64_t* result, const uint64_t* operand1, ui
                                   uint64_t modulus, int cmp, uint64_t bound, uint64_t diff,
                                   void* stream);
 
+/* ---- Montgomery-form helpers (R = 2^r > q, q odd, r <= 62: the BitShift = 64 forms of the reference)
+ * HenselLemma2adicRoot (number-theory.hpp:303): x in [0, 2^r) with q*x = -1 mod 2^r; 0 for invalid arguments */
+uint64_t hexl_b200_hensel_lemma_2adic_root(uint32_t r, uint64_t q);
+/* MontgomeryReduce<64> (number-theory.hpp:269-301): T * 2^-r mod q for T = T_hi*2^64 + T_lo < q * 2^r */
+uint64_t hexl_b200_montgomery_reduce(uint64_t T_hi, uint64_t T_lo, uint64_t q, int r, uint64_t inv_mod);
+/* EltwiseMontReduceModAVX512<64, r> (hexl/eltwise/eltwise-reduce-mod-avx512.hpp:156): result = a*b*R^-1 mod q;
+ * EltwiseMontgomeryFormInAVX512 (:227): result = a*R mod q, given R^2 mod q;
+ * EltwiseMontgomeryFormOutAVX512 (:298): result = a*R^-1 mod q.  Inputs < q, outputs in [0, q). */
+int hexl_b200_eltwise_mont_reduce_mod(uint64_t* result, const uint64_t* a, const uint64_t* b, uint64_t n,
+                                      uint64_t modulus, int r, uint64_t neg_inv_mod, void* stream);
+int hexl_b200_eltwise_montgomery_form_in(uint64_t* result, const uint64_t* a, uint64_t R2_mod_q, uint64_t n,
+                                         uint64_t modulus, int r, uint64_t neg_inv_mod, void* stream);
+int hexl_b200_eltwise_montgomery_form_out(uint64_t* result, const uint64_t* a, uint64_t n, uint64_t modulus, int r,
+                                          uint64_t neg_inv_mod, void* stream);
+
 /* ---- SEAL-shaped composites built on the hot path (hexl/include/hexl/experimental/seal/)
  * `moduli`, `modswitch_factors` and the array `k_switch_keys` itself are small HOST
  * arrays; the coefficient buffers (result, operands, t_target, every k_switch_keys[j])

@@ -92,6 +92,11 @@ class Port:
         L.orc_eltwise_reduce_mod.argtypes = [vp, vp, u64, u64, u64, u64]
         L.orc_eltwise_cmp_add.argtypes = [vp, vp, u64, C.c_int, u64, u64]
         L.orc_eltwise_cmp_sub_mod.argtypes = [vp, vp, u64, u64, C.c_int, u64, u64]
+        L.orc_hensel_lemma_2adic_root.restype, L.orc_hensel_lemma_2adic_root.argtypes = u64, [C.c_uint32, u64]
+        L.orc_montgomery_reduce.restype, L.orc_montgomery_reduce.argtypes = u64, [u64, u64, u64, C.c_int, u64]
+        L.orc_eltwise_mont_reduce_mod.argtypes = [vp, vp, vp, u64, u64, C.c_int, u64]
+        L.orc_eltwise_montgomery_form_in.argtypes = [vp, vp, u64, u64, u64, C.c_int, u64]
+        L.orc_eltwise_montgomery_form_out.argtypes = [vp, vp, u64, u64, C.c_int, u64]
         L.orc_dyadic_multiply.argtypes = [vp, vp, vp, u64, vp, u64]
         L.orc_key_switch.argtypes = [vp, vp, u64, u64, u64, u64, u64, vp, vp, vp]
         self._tables = {}
@@ -110,6 +115,28 @@ class Port:
         got = self.L.orc_generate_primes(_ptr(out), num, bits, int(prefer_small), ntt_size)
         assert got == num, "not enough primes"
         return [int(v) for v in out]
+
+    # -- Montgomery-form helpers
+    def hensel_lemma_2adic_root(self, r, q): return self.L.orc_hensel_lemma_2adic_root(r, q)
+    def montgomery_reduce(self, t_hi, t_lo, q, r, inv_mod): return self.L.orc_montgomery_reduce(t_hi, t_lo, q, r, inv_mod)
+
+    def mont_reduce_mod(self, a, b, q, r, inv_mod):
+        a = np.ascontiguousarray(a, dtype=np.uint64); b = np.ascontiguousarray(b, dtype=np.uint64)
+        res = np.empty_like(a)
+        self.L.orc_eltwise_mont_reduce_mod(_ptr(res), _ptr(a), _ptr(b), a.size, q, r, inv_mod)
+        return res
+
+    def montgomery_form_in(self, a, r2_mod_q, q, r, inv_mod):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        res = np.empty_like(a)
+        self.L.orc_eltwise_montgomery_form_in(_ptr(res), _ptr(a), r2_mod_q, a.size, q, r, inv_mod)
+        return res
+
+    def montgomery_form_out(self, a, q, r, inv_mod):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        res = np.empty_like(a)
+        self.L.orc_eltwise_montgomery_form_out(_ptr(res), _ptr(a), a.size, q, r, inv_mod)
+        return res
 
     # -- tables / transforms
     def tables(self, n, q, root=None):
@@ -283,6 +310,12 @@ class Ref:
         L.ref_eltwise_reduce_mod_native.argtypes = [vp, vp, u64, u64, u64, u64]
         L.ref_eltwise_cmp_add_native.argtypes = [vp, vp, u64, C.c_int, u64, u64]
         L.ref_eltwise_cmp_sub_mod_native.argtypes = [vp, vp, u64, u64, C.c_int, u64, u64]
+        self.has_mont = hasattr(L, "ref_eltwise_montgomery")
+        if self.has_mont:
+            L.ref_hensel_lemma_2adic_root.restype, L.ref_hensel_lemma_2adic_root.argtypes = u64, [C.c_uint32, u64]
+            L.ref_montgomery_reduce.restype, L.ref_montgomery_reduce.argtypes = u64, [u64, u64, u64, C.c_int, u64]
+            L.ref_eltwise_montgomery.restype = C.c_int
+            L.ref_eltwise_montgomery.argtypes = [C.c_int, vp, vp, vp, u64, u64, C.c_int, u64]
         self.has_seal = hasattr(L, "ref_key_switch")
         if self.has_seal:
             L.ref_dyadic_multiply.argtypes = [vp, vp, vp, u64, vp, u64]
@@ -439,6 +472,19 @@ class Ref:
         return r
 
 
+def _ref_mont(self, kind, a, b, q, r, inv_mod):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64)
+    res = np.empty_like(a)
+    self.last_mont_was_avx512 = bool(self.L.ref_eltwise_montgomery(kind, _ptr(res), _ptr(a), _ptr(b), a.size, q, r, inv_mod))
+    return res
+
+
+Ref.hensel_lemma_2adic_root = lambda self, r, q: self.L.ref_hensel_lemma_2adic_root(r, q)
+Ref.montgomery_reduce = lambda self, t_hi, t_lo, q, r, inv_mod: self.L.ref_montgomery_reduce(t_hi, t_lo, q, r, inv_mod)
+Ref.mont_reduce_mod = lambda self, a, b, q, r, inv_mod: _ref_mont(self, 0, a, b, q, r, inv_mod)
+Ref.montgomery_form_in = lambda self, a, r2_mod_q, q, r, inv_mod: _ref_mont(self, 1, a, np.array([r2_mod_q], dtype=np.uint64), q, r, inv_mod)
+Ref.montgomery_form_out = lambda self, a, q, r, inv_mod: _ref_mont(self, 2, a, np.zeros(1, dtype=np.uint64), q, r, inv_mod)
 Ref.dyadic_multiply = lambda self, op1, op2, n, moduli: _dyadic_call(self.L.ref_dyadic_multiply, op1, op2, n, moduli)
 Ref.key_switch = lambda self, result, t_target, n, decomp, key_mod, rns, kcc, moduli, keys, modswitch: _key_switch_call(
     self.L.ref_key_switch, result, t_target, n, decomp, key_mod, rns, kcc, moduli, keys, modswitch)

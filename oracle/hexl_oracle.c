@@ -459,6 +459,54 @@ void orc_eltwise_reduce_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_t
   }
 }
 
+/* ---- Montgomery-form helpers.
+ * HenselLemma2adicRoot, hexl/include/hexl/number-theory/number-theory.hpp:303-336: the x in [0, 2^r) with
+ * q*x = -1 mod 2^r, lifted one bit at a time. */
+uint64_t orc_hensel_lemma_2adic_root(uint32_t r, uint64_t q) {
+  uint64_t a_prev = 1, c = 2, mod_mask = 3;
+  for (uint64_t k = 2; k <= r; ++k) {
+    uint64_t f, t = 0, a;
+    do {
+      a = a_prev + c * t++;
+      f = q * a + 1ULL;
+    } while (f & mod_mask);
+    mod_mask = mod_mask * 2 + 1ULL;
+    c *= 2;
+    a_prev = a;
+  }
+  return a_prev;
+}
+/* MontgomeryReduce<64>, number-theory.hpp:269-301: T = T_hi*2^64 + T_lo < q*R, R = 2^r > q, q*inv_mod = -1 mod R;
+ * returns T * R^-1 mod q in [0, q). */
+uint64_t orc_montgomery_reduce(uint64_t T_hi, uint64_t T_lo, uint64_t q, int r, uint64_t inv_mod) {
+  const uint64_t mask = (1ULL << r) - 1;
+  const uint64_t m = ((T_lo & mask) * inv_mod) & mask;
+  const u128 mq = (u128)m * q;
+  const u128 t = (((u128)T_hi << 64) | T_lo) + mq;   /* < 2 q R <= 2^125: no overflow */
+  const uint64_t s = (uint64_t)(t >> r);
+  return s >= q ? s - q : s;
+}
+/* EltwiseMontReduceModAVX512<64, r>, hexl/eltwise/eltwise-reduce-mod-avx512.hpp:156-225: a[i]*b[i]*R^-1 mod q */
+void orc_eltwise_mont_reduce_mod(uint64_t* res, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t q, int r,
+                                 uint64_t inv_mod) {
+  for (uint64_t i = 0; i < n; ++i) {
+    const u128 T = (u128)a[i] * b[i];
+    res[i] = orc_montgomery_reduce((uint64_t)(T >> 64), (uint64_t)T, q, r, inv_mod);
+  }
+}
+/* EltwiseMontgomeryFormInAVX512<64, r>, :227-296: a[i]*R mod q = REDC(a[i] * (R^2 mod q)) */
+void orc_eltwise_montgomery_form_in(uint64_t* res, const uint64_t* a, uint64_t R2_mod_q, uint64_t n, uint64_t q, int r,
+                                    uint64_t inv_mod) {
+  for (uint64_t i = 0; i < n; ++i) {
+    const u128 T = (u128)a[i] * R2_mod_q;
+    res[i] = orc_montgomery_reduce((uint64_t)(T >> 64), (uint64_t)T, q, r, inv_mod);
+  }
+}
+/* EltwiseMontgomeryFormOutAVX512<64, r>, :298-352: a[i]*R^-1 mod q = REDC(a[i]) */
+void orc_eltwise_montgomery_form_out(uint64_t* res, const uint64_t* a, uint64_t n, uint64_t q, int r, uint64_t inv_mod) {
+  for (uint64_t i = 0; i < n; ++i) res[i] = orc_montgomery_reduce(0, a[i], q, r, inv_mod);
+}
+
 /* hexl/util/util-internal.hpp:16-42, enum values hexl/include/hexl/util/util.hpp:16-25 */
 static inline int cmp_holds(int cmp, uint64_t lhs, uint64_t rhs) {
   switch (cmp) {

@@ -58,6 +58,15 @@ void orc_eltwise_cmp_add(uint64_t* r, const uint64_t* a, uint64_t n, int cmp, ui
 void orc_eltwise_cmp_sub_mod(uint64_t* r, const uint64_t* a, uint64_t n, uint64_t q, int cmp,
                              uint64_t bound, uint64_t diff);
 
+/* Montgomery-form helpers (number-theory.hpp:269-336; eltwise-reduce-mod-avx512.hpp:156-352, BitShift 64) */
+uint64_t orc_hensel_lemma_2adic_root(uint32_t r, uint64_t q);
+uint64_t orc_montgomery_reduce(uint64_t T_hi, uint64_t T_lo, uint64_t q, int r, uint64_t inv_mod);
+void orc_eltwise_mont_reduce_mod(uint64_t* res, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t q, int r,
+                                 uint64_t inv_mod);
+void orc_eltwise_montgomery_form_in(uint64_t* res, const uint64_t* a, uint64_t R2_mod_q, uint64_t n, uint64_t q, int r,
+                                    uint64_t inv_mod);
+void orc_eltwise_montgomery_form_out(uint64_t* res, const uint64_t* a, uint64_t n, uint64_t q, int r, uint64_t inv_mod);
+
 /* SEAL-shaped composites (reference: hexl/experimental/seal/) */
 void orc_dyadic_multiply(uint64_t* result, const uint64_t* operand1, const uint64_t* operand2,
                          uint64_t n, const uint64_t* moduli, uint64_t num_moduli);

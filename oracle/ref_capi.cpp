@@ -34,6 +34,9 @@
 #include "hexl/util/util.hpp"
 #include "ntt/ntt-internal.hpp"
 #include "util/cpu-features.hpp"
+#ifdef HEXL_HAS_AVX512DQ
+#include "eltwise/eltwise-reduce-mod-avx512.hpp"
+#endif
 
 using namespace intel::hexl;
 
@@ -271,6 +274,40 @@ void ref_eltwise_cmp_sub_mod_native(uint64_t* r, const uint64_t* a, uint64_t n,
                                     uint64_t q, int cmp, uint64_t bound,
                                     uint64_t diff) {
   EltwiseCmpSubModNative(r, a, n, q, static_cast<CMPINT>(cmp), bound, diff);
+}
+
+// ---- Montgomery-form helpers: the reference's scalar definitions (number-theory.hpp:269-336) for any r, and its
+// AVX-512 element-wise helpers (eltwise/eltwise-reduce-mod-avx512.hpp:156-352) for the two r its own tests use.
+uint64_t ref_hensel_lemma_2adic_root(uint32_t r, uint64_t q) { return HenselLemma2adicRoot(r, q); }
+uint64_t ref_montgomery_reduce(uint64_t T_hi, uint64_t T_lo, uint64_t q, int r, uint64_t inv_mod) {
+  return MontgomeryReduce<64>(T_hi, T_lo, q, r, (1ULL << r) - 1, inv_mod);
+}
+// kind: 0 = a*b*R^-1, 1 = a*R (b[0] = R^2 mod q), 2 = a*R^-1.  Returns 1 when the AVX-512 helper ran, 0 for the scalar loop.
+int ref_eltwise_montgomery(int kind, uint64_t* res, const uint64_t* a, const uint64_t* b, uint64_t n, uint64_t q, int r,
+                           uint64_t inv_mod) {
+#ifdef HEXL_HAS_AVX512DQ
+  if (has_avx512dq && (r == 46 || r == 61)) {
+    if (kind == 0) {
+      if (r == 46) EltwiseMontReduceModAVX512<64, 46>(res, a, b, n, q, inv_mod);
+      else EltwiseMontReduceModAVX512<64, 61>(res, a, b, n, q, inv_mod);
+    } else if (kind == 1) {
+      if (r == 46) EltwiseMontgomeryFormInAVX512<64, 46>(res, a, b[0], n, q, inv_mod);
+      else EltwiseMontgomeryFormInAVX512<64, 61>(res, a, b[0], n, q, inv_mod);
+    } else {
+      if (r == 46) EltwiseMontgomeryFormOutAVX512<64, 46>(res, a, n, q, inv_mod);
+      else EltwiseMontgomeryFormOutAVX512<64, 61>(res, a, n, q, inv_mod);
+    }
+    return 1;
+  }
+#endif
+  const uint64_t mask = (1ULL << r) - 1;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint64_t hi = 0, lo = a[i];
+    if (kind == 0) MultiplyUInt64(a[i], b[i], &hi, &lo);
+    if (kind == 1) MultiplyUInt64(a[i], b[0], &hi, &lo);
+    res[i] = MontgomeryReduce<64>(hi, lo, q, r, mask, inv_mod);
+  }
+  return 0;
 }
 
 // ---- SEAL-shaped composites (hexl/include/hexl/experimental/seal/*.hpp) --------

@@ -168,7 +168,11 @@ def test_ntt_extreme_inputs(hb, checker):
                     assert (got < np.uint64(2 * q)).all()
 
 
-@pytest.mark.parametrize("env", [{"HEXL_B200_DSMEM": "2"},
+@pytest.mark.parametrize("env", [{"HEXL_B200_PIPE": "1", "HEXL_B200_PIPE_MIN_BATCH": "1"},
+                                 {"HEXL_B200_PIPE": "1", "HEXL_B200_PIPE_MIN_BATCH": "1", "HEXL_B200_PIPE_LOOKAHEAD": "1",
+                                  "HEXL_B200_PIPE_CTAS": "1"},
+                                 {"HEXL_B200_PIPE": "0"},
+                                 {"HEXL_B200_DSMEM": "2"},
                                  {"HEXL_B200_FUSED": "1", "HEXL_B200_FUSED_SMALL": "1", "HEXL_B200_DSMEM": "0"},
                                  {"HEXL_B200_FUSED": "0", "HEXL_B200_FUSED_SMALL": "0", "HEXL_B200_DSMEM": "0"},
                                  {"HEXL_B200_FORCE_GENERIC": "1", "HEXL_B200_NO_WIDE": "1"}])

@@ -136,6 +136,14 @@ __device__ __forceinline__ void bf15(u64& X, u64& Y, Tw w, const Mod& m) {
   u64 T = mad_chain5(Y, w.w, Q, m);
   Y = X + m.four_q - T; X = X + T;
 }
+// ---- variant 16: Montgomery butterfly (R = 2^64, twiddle in Montgomery form, lazy [0,2q) output) -- SURVEY 8(f)-4:
+//   P = Y*W (128 bits), m = lo(P) * (-q^-1) mod 2^64, T = hi(P) + hi(m*q) + (lo(P) != 0)  in [0, 2q)
+__device__ __forceinline__ void bf16(u64& X, u64& Y, Tw w, const Mod& m) {
+  const u64 plo = Y * w.w, phi = __umul64hi(Y, w.w);
+  const u64 mm = plo * m.mu;                      // m.mu stands in for -q^-1 mod 2^64
+  const u64 T = phi + __umul64hi(mm, m.q) + (plo != 0);
+  Y = X + m.two_q - T; X = X + T;
+}
 // ---- variant 6: exact mulhi (compiler's __umul64hi) + pinned mad chain, no csub (FAST-exact)
 __device__ __forceinline__ void bf6(u64& X, u64& Y, Tw w, const Mod& m) {
   u64 T = mad_chain5(Y, w.w, __umul64hi(Y, w.wp), m);
@@ -260,6 +268,7 @@ template <int MINB, int VAR = 10> void run10(const char* name, u64* out, const T
 
 template <int V> __device__ __forceinline__ void bf(u64& X, u64& Y, Tw w, const Mod& m) {
   if (V == 5) { bf5(X, Y, w, m); return; } if (V == 6) { bf6(X, Y, w, m); return; }
+  if (V == 16) { bf16(X, Y, w, m); return; }
   if (V == 14) { bf14(X, Y, w, m); return; } if (V == 15) { bf15(X, Y, w, m); return; }
   if (V == 12) { bf12(X, Y, w, m); return; } if (V == 13) { bf13(X, Y, w, m); return; }
   if (V == 7) { bf7(X, Y, w, m); return; } if (V == 8) { bf8(X, Y, w, m); return; }
@@ -396,6 +405,8 @@ int main() {
   run<14, 3>("v14 mb3", out, tw, m, 3);
   run<15, 2>("v15 hs via add.cc", out, tw, m, 2);
   run<15, 3>("v15 mb3", out, tw, m, 3);
+  run<16, 2>("v16 Montgomery R=2^64", out, tw, m, 2);
+  run<16, 3>("v16 mb3", out, tw, m, 3);
   run<13, 2>("v13 IMAD.HI + plain adds", out, tw, m, 2);
   run<13, 3>("v13 mb3", out, tw, m, 3);
   run<5, 3>("v5 mb3", out, tw, m, 3);
