@@ -125,14 +125,14 @@ cudaError_t launch_fused(bool fwd, const NttDeviceTables& t, u64* result, const 
 }
 
 // The persistent pipelined kernel: one launch, work items from a global counter (ntt_kernels.cuh).
-// HEXL_B200_PIPE: 1 = use it for N = 2^14 .. 2^17 (default), 0 = off; HEXL_B200_PIPE_LOOKAHEAD = polynomials
-// between a producer block and its consumers (default 16), HEXL_B200_PIPE_CTAS = CTAs per SM (default: the
+// HEXL_B200_PIPE: see pipe_log_r below; HEXL_B200_PIPE_LOOKAHEAD = polynomials
+// between a producer block and its consumers (default 48), HEXL_B200_PIPE_CTAS = CTAs per SM (default: the
 // kernel's launch bound).
 template <int MODE, int LOGR>
 cudaError_t launch_pipe(bool fwd, const NttDeviceTables& t, u64* result, const u64* operand, u64 batch, int out_mf,
                         cudaStream_t stream) {
   using Cfg = PipeCfg<LOGR, MODE>;
-  static const int lookahead_env = env_int("HEXL_B200_PIPE_LOOKAHEAD", 16);
+  static const int lookahead_env = env_int("HEXL_B200_PIPE_LOOKAHEAD", 48);
   static const int ctas_env = env_int("HEXL_B200_PIPE_CTAS", 0);
   const Mod m = make_mod(t);
   int dev = 0, sms = 0;
@@ -175,13 +175,21 @@ cudaError_t launch_pipe_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64* 
   return cudaErrorInvalidValue;
 }
 
-// log2(N / 4096) for which the pipelined kernel is used; 0 = none.  A batch of fewer polynomials than the
-// pipeline is deep gains nothing from it.
-inline int pipe_log_r(int log_n, u64 batch) {
-  static const int mode = env_int("HEXL_B200_PIPE", 0);
+// log2(N / 4096) for which the pipelined kernel is used; 0 = none.  HEXL_B200_PIPE: 1 = always (N = 2^14..2^17),
+// 0 = never, unset = where it measured faster than the two-kernel split on B200 (profiles/r2e_pipe_lookahead_sweep.txt,
+// r2d_pipe_vs_split.txt; 2^28 coefficients): forward N = 2^17 (55-bit 3.02 vs 3.20 ms, 29-bit 1.34 vs 1.38) and the
+// 32-bit-word inverse at N >= 2^16 (1.35 vs 1.42, 1.46 vs 1.52).  Elsewhere the split is 2-4 % faster although it
+// moves twice the HBM bytes: the transforms are bound by instruction issue, not by memory.  A batch of fewer
+// polynomials than the pipeline is deep gains nothing from it.
+template <int MODE>
+inline int pipe_log_r(int log_n, u64 batch, bool forward) {
+  static const int mode = env_int("HEXL_B200_PIPE", -1);
   static const int min_batch = env_int("HEXL_B200_PIPE_MIN_BATCH", 64);
   const int lr = log_n - 12;
-  return (mode != 0 && lr >= 2 && lr <= 5 && batch >= (u64)min_batch && batch < (1ull << 31)) ? lr : 0;
+  if (mode == 0 || lr < 2 || lr > 5 || batch < (u64)min_batch || batch >= (1ull << 31)) return 0;
+  if (mode > 0) return lr;
+  const bool wins = (forward && log_n == 17) || (MODE == kSmall && !forward && log_n >= 16);
+  return wins ? lr : 0;
 }
 
 // SMALL mode: the single kernel that keeps the intermediate in the cluster's shared memory
@@ -259,7 +267,7 @@ cudaError_t launch_fused_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64*
 template <int MODE>
 cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
-  if (const int lr = pipe_log_r(t.log_n, batch)) return launch_pipe_dyn<MODE>(lr, true, t, result, operand, batch, out_mf, stream);
+  if (const int lr = pipe_log_r<MODE>(t.log_n, batch, true)) return launch_pipe_dyn<MODE>(lr, true, t, result, operand, batch, out_mf, stream);
   if constexpr (MODE == kSmall)
     if (const int lr = dsmem_log_r(t.log_n)) return launch_dsmem_dyn(lr, true, t, result, operand, batch, out_mf, stream);
   if (const int lr = fused_log_r<MODE>(t.log_n)) return launch_fused_dyn<MODE>(lr, true, t, result, operand, batch, out_mf, stream);
@@ -280,7 +288,7 @@ cudaError_t forward_impl(const NttDeviceTables& t, u64* result, const u64* opera
 template <int MODE>
 cudaError_t inverse_impl(const NttDeviceTables& t, u64* result, const u64* operand, int out_mf,
                          u64 batch, cudaStream_t stream) {
-  if (const int lr = pipe_log_r(t.log_n, batch)) return launch_pipe_dyn<MODE>(lr, false, t, result, operand, batch, out_mf, stream);
+  if (const int lr = pipe_log_r<MODE>(t.log_n, batch, false)) return launch_pipe_dyn<MODE>(lr, false, t, result, operand, batch, out_mf, stream);
   if constexpr (MODE == kSmall)
     if (const int lr = dsmem_log_r(t.log_n)) return launch_dsmem_dyn(lr, false, t, result, operand, batch, out_mf, stream);
   if (const int lr = fused_log_r<MODE>(t.log_n)) return launch_fused_dyn<MODE>(lr, false, t, result, operand, batch, out_mf, stream);

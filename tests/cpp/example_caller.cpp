@@ -155,6 +155,47 @@ int main(int argc, char** argv) {
       NTT::ComputeInverseMulti(list, 2, v.data(), v.data(), 1, 1, 2);
       Expect(v, orig, "multi-modulus round trip");
     }
+    {
+      // Montgomery form in and out (test/test-eltwise-reduce-mod-avx512.cpp:38-64, r = 46) and a Montgomery product
+      const uint64_t modulus = 67280421310725ULL;
+      const int r = 46;
+      std::vector<uint64_t> in{0, 67280421310000, 25040294381203, 340231313, 769231483400, 90032324, 120042353, 1530};
+      std::vector<uint64_t> out(in.size()), prod(in.size()), plain(in.size());
+      const uint64_t R_reduced = (1ULL << r) % modulus;
+      const uint64_t R2 = MultiplyMod(R_reduced, R_reduced, modulus);
+      const uint64_t inv_mod = HenselLemma2adicRoot(r, modulus);
+      if (inv_mod != 62463730494515ULL) ++failures;  // test/test-avx512-util.cpp:417
+      EltwiseMontgomeryFormIn(out.data(), in.data(), R2, in.size(), modulus, r, inv_mod);
+      EltwiseMontReduceMod(prod.data(), out.data(), in.data(), in.size(), modulus, r, inv_mod);  // (aR)(a)/R = a*a
+      EltwiseMultMod(plain.data(), in.data(), in.data(), in.size(), modulus, 1);
+      Expect(prod, plain, "Montgomery product");
+      EltwiseMontgomeryFormOut(out.data(), out.data(), in.size(), modulus, r, inv_mod);
+      Expect(out, in, "Montgomery form in/out");
+    }
+    {
+      // KeySwitch against keys uploaded once equals KeySwitch with the keys in caller memory
+      const uint64_t n = 64, decomp = 2, kms = 3, rns = 3, kcc = 2;
+      std::vector<uint64_t> moduli = GeneratePrimes(kms, 40, true, n);
+      std::vector<std::vector<uint64_t>> keys(decomp, std::vector<uint64_t>(kcc * kms * n));
+      for (uint64_t j = 0; j < decomp; ++j)
+        for (uint64_t k = 0; k < kcc; ++k)
+          for (uint64_t i = 0; i < kms; ++i)
+            for (uint64_t l = 0; l < n; ++l) keys[j][(k * kms + i) * n + l] = (j * 1315423911ULL + k * 2654435761ULL + i * 97 + l * l + 3) % moduli[i];
+      const uint64_t* key_ptrs[2] = {keys[0].data(), keys[1].data()};
+      std::vector<uint64_t> t(decomp * n), res(kcc * decomp * n), res2, modswitch(decomp);
+      for (uint64_t j = 0; j < decomp; ++j) {
+        modswitch[j] = InverseMod(moduli[kms - 1] % moduli[j], moduli[j]);
+        for (uint64_t l = 0; l < n; ++l) t[j * n + l] = (l * 7919 + j) % moduli[j];
+      }
+      for (uint64_t k = 0; k < kcc; ++k)
+        for (uint64_t i = 0; i < decomp; ++i)
+          for (uint64_t l = 0; l < n; ++l) res[(k * decomp + i) * n + l] = (l * 104729 + k * 31 + i) % moduli[i];
+      res2 = res;
+      KeySwitch(res.data(), t.data(), n, decomp, kms, rns, kcc, moduli.data(), key_ptrs, modswitch.data());
+      b200::KeySwitchKeys resident(key_ptrs, n, decomp, kms, kcc);
+      KeySwitch(res2.data(), t.data(), n, decomp, kms, rns, kcc, moduli.data(), resident, modswitch.data());
+      Expect(res2, res, "KeySwitch with resident keys");
+    }
     bool threw = false;
     try {
       std::vector<uint64_t> a{1, 2};

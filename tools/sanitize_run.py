@@ -45,5 +45,23 @@ res = torch.cat([torch.randint(0, mods[i], (n,), dtype=torch.int64, device="cuda
 hb.KeySwitch(res, tt, n, decomp, kms, rns, kcc, mods, keys, [hb.InverseMod(mods[-1] % mods[i], mods[i]) for i in range(decomp)])
 h = np.arange(n, dtype=np.uint64) % np.uint64(mods[0])
 ntts[0].ComputeForward(h, h, 1, 1)  # host-pointer staging path
+# round 2: resident keys (device and host buffers, two ciphertexts), composite host paths, Montgomery helpers
+modswitch = [hb.InverseMod(mods[-1] % mods[i], mods[i]) for i in range(decomp)]
+kh = hb.KeySwitchKeys(keys, n, decomp, kms, kcc)
+hb.KeySwitchResident(torch.cat([res, res]), torch.cat([tt, tt]), n, decomp, kms, rns, kcc, mods, kh, modswitch, 2)
+hres = np.concatenate([res.cpu().numpy().view(np.uint64)] * 2)
+hb.KeySwitchResident(hres, np.concatenate([tt.cpu().numpy().view(np.uint64)] * 2), n, decomp, kms, rns, kcc, mods, kh, modswitch, 2)
+ha, hbb = a.cpu().numpy().view(np.uint64), b.cpu().numpy().view(np.uint64)
+ho = np.zeros_like(ha)
+hb.PolyMultiplyMulti(ntts, ho, ha, hbb, 2)
+hb.ComputeForwardMulti(ntts, ho, ha, 1, 4, batch_per_modulus=2)
+hb.EltwiseMultModMulti(ho, ha, hbb, 2 * n, mods)
+hout = np.zeros(3 * n * 3, dtype=np.uint64)
+hb.DyadicMultiply(hout, ha, hbb, n, mods)
+qm, r = mods[0], 61
+inv = hb.HenselLemma2adicRoot(r, qm)
+hb.EltwiseMontgomeryFormIn(o, a, (1 << r) * (1 << r) % qm, 2 * n, qm, r, inv)
+hb.EltwiseMontReduceMod(o, o, b, 2 * n, qm, r, inv)
+hb.EltwiseMontgomeryFormOut(o, o, 2 * n, qm, r, inv)
 torch.cuda.synchronize()
 print("sanitize workload done")

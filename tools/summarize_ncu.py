@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Summarise ncu artefacts from gpurun_out/ into profiles/ (tracked).
 
-  python tools/summarize_ncu.py <tag> <launches.csv> <full.ncu-rep>
+  python tools/summarize_ncu.py <tag> <launches.csv> <full.ncu-rep | raw.csv>... [--batch B]
+
+A capture may be given as the .ncu-rep or as its `ncu -i x.ncu-rep --page raw --csv` export (what the GPU box
+sends back: the reports themselves exceed gpurun's 64 MiB return limit).  --batch = polynomials per NTT launch
+of the profiled command (bench.py default 8192), recorded so that bench.py can scale the traffic to its batch.
 
 Writes profiles/<tag>_launches.md (per-kernel launch times and share of the step),
 profiles/<tag>_ncu.md (roofline-relevant metrics per kernel) and refreshes
@@ -15,8 +19,15 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag, launches = sys.argv[1:3]
-reps = sys.argv[3:]
+args = sys.argv[1:]
+batch = 8192
+if "--batch" in args:
+    i = args.index("--batch")
+    batch = int(args[i + 1])
+    del args[i:i + 2]
+tag, launches = args[:2]
+reps = args[2:]
+sys.path.insert(0, ROOT)
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
@@ -52,7 +63,10 @@ with open(os.path.join(out_dir, f"{tag}_launches.md"), "w") as f:
 # ---- full capture
 rows = []
 for rep in reps:
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     part = list(csv.reader(raw.splitlines()))
     if not rows:
         rows = part
@@ -105,10 +119,13 @@ with open(os.path.join(out_dir, f"{tag}_ncu.md"), "w") as f:
         rd = num("dram__bytes_read.sum") * unit.get(U[H.index("dram__bytes_read.sum")], 1.0)
         wr = num("dram__bytes_write.sum") * unit.get(U[H.index("dram__bytes_write.sum")], 1.0)
         traffic[k] = rd + wr
-fwd = sum(v for k, v in traffic.items() if k.startswith("ntt_row_fwd") or (k.startswith("ntt_col") and k.rstrip(">").endswith("1")))
-json.dump({"tag": tag, "dram_bytes_per_launch": traffic, "ntt_forward_bytes_per_launch": fwd,
+fwd = sum(v for k, v in traffic.items() if k.startswith(("ntt_row_fwd", "ntt_pipe_fwd", "ntt_fused_fwd", "ntt_dsmem_fwd"))
+          or (k.startswith("ntt_col") and k.rstrip(">").endswith("1")))
+import bench  # noqa: E402  (source_hash: the capture is only believed on the kernel sources it was taken on)
+json.dump({"tag": tag, "source_hash": bench.source_hash(), "batch": batch, "dram_bytes_per_launch": traffic,
+           "ntt_forward_bytes_per_launch": fwd, "ntt_forward_bytes_per_polynomial": fwd / batch,
            "note": "dram__bytes_read.sum + dram__bytes_write.sum from one ncu --set full capture; "
-                   "ntt_forward = column pass + row kernel of one hexl_b200_ntt_forward call"},
+                   "ntt_forward = all kernels of one hexl_b200_ntt_forward call"},
           open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out_dir, f"{tag}_launches.md")).read())
 print({k: round(v / 1e9, 3) for k, v in traffic.items()}, "fwd", fwd / 1e9)
