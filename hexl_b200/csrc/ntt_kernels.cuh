@@ -34,6 +34,13 @@
 
 #include "internal.h"
 
+// Timing-only ablations of the row kernels (results are WRONG when any bit is set; used by tools/ablate.sh to
+// attribute the kernel's time): 1 = no global loads, 2 = no global stores, 4 = last-pass twiddles not from L2,
+// 8 = no shared-memory exchanges, 16 = no twiddle tables in shared memory (and no barrier for them)
+#ifndef HEXL_B200_ABLATE
+#define HEXL_B200_ABLATE 0
+#endif
+
 namespace hexl_b200 {
 namespace {
 
@@ -512,6 +519,8 @@ __device__ __forceinline__ void reg_stages(typename Ar<MODE>::E (&v)[16], unsign
       for (int g = 0; g < (8 >> eb); ++g) {
         if (PT::kShared)
           wc[g] = sroot[(8 >> eb) + g];             // local node 2^s' + g, s' = 3 - eb
+        else if (HEXL_B200_ABLATE & 4)
+          wc[g] = stab[((8 >> eb) + g + (u & 15) * 16) & 255];
         else
           wc[g] = ld_tw(tw + stage_node0(step) + g);
       }
@@ -542,6 +551,7 @@ __device__ __forceinline__ void reg_stages(typename Ar<MODE>::E (&v)[16], unsign
 template <int LB_FROM, int LB_TO, typename E>
 __device__ __forceinline__ void smem_exchange(E (&v)[16], E* srow, unsigned u) {
   constexpr bool kWarpLocal = (LB_FROM > LB_TO ? LB_FROM : LB_TO) <= 5;
+  if (HEXL_B200_ABLATE & 8) return;
 #pragma unroll
   for (int e = 0; e < 16; ++e) srow[swz<E>(reg_index<LB_FROM>(u, e))] = v[e];
   if (kWarpLocal)
@@ -658,13 +668,20 @@ __device__ __forceinline__ void row_fwd_body(void* out, const void* in, typename
   // filled by all threads of the CTA instead of one per row
   Tw* stab = cta_stab ? cta_stab : reinterpret_cast<Tw*>(srow + (1 << LOGC));
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = ld_row<LD, E>(in, reg_index<LB0>(u, e));
-  if constexpr (RowCfg<LOGC>::TW_TABLES) {
-    if (cta_stab)
-      load_row_twiddles<LOGC>(stab, threadIdx.x, blockDim.x, base, tw);
+  for (int e = 0; e < 16; ++e) {
+    if (HEXL_B200_ABLATE & 1)
+      v[e] = (E)((u * 16 + e) * 0x9E3779B97F4A7C15ull + base) & (E)(m.q - 1);
     else
-      load_row_twiddles<LOGC>(stab, u, (1u << LOGC) / 16, base, tw);
-    __syncthreads();
+      v[e] = ld_row<LD, E>(in, reg_index<LB0>(u, e));
+  }
+  if constexpr (RowCfg<LOGC>::TW_TABLES) {
+    if (!(HEXL_B200_ABLATE & 16)) {
+      if (cta_stab)
+        load_row_twiddles<LOGC>(stab, threadIdx.x, blockDim.x, base, tw);
+      else
+        load_row_twiddles<LOGC>(stab, u, (1u << LOGC) / 16, base, tw);
+      __syncthreads();
+    }
   }
   reg_stages<MODE, LOGC, LB0, LOGC - 1, LB0, true>(v, u, base, tw, stab, m, false, Tw{}, Tw{});
   fwd_passes<MODE, LOGC, 1>(v, srow, u, base, tw, stab, m);
@@ -677,7 +694,8 @@ __device__ __forceinline__ void row_fwd_body(void* out, const void* in, typename
   if constexpr (LOGC > 4) smem_exchange<0, LB_OUT>(v, srow, u);
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) st_row<ST, E>(out, reg_index<LB_OUT>(u, e), v[e]);
+    for (int e = 0; e < 16; ++e)
+      if (!(HEXL_B200_ABLATE & 2) || v[e] == (E)0x123456789abcdefull) st_row<ST, E>(out, reg_index<LB_OUT>(u, e), v[e]);
   }
 }
 
