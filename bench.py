@@ -422,6 +422,37 @@ def c5_leg(args, hb, torch, rank, world, gen, sync, cpu_ok):
         dt = max_over_ranks((time.perf_counter() - t0) / 3, world)
         out["e2e"] = {"value": world * cts / dt, "unit": "key switches/s", "ms_per_key_switch": dt * 1e3 / cts,
                       "h2d_bytes_per_step": 8 * (t_all.numel() + r0.numel()), "d2h_bytes_per_step": 8 * r0.numel()}
+        # latency of ONE switch from host buffers (what a reference-shaped caller sees): keys resident on one GPU, and --
+        # when this single process sees several GPUs -- the moduli of the switch sharded over all of them (digit
+        # all-gather + special-prime broadcast over NVLink peer copies)
+        if world == 1:
+            one = lambda h: hb.KeySwitchResident(hr[:r0.numel() // cts], ht[:t_all.numel() // cts], n, decomp, kms, rns, kcc,
+                                                 mods, h, modswitch, 1)
+            one(handle); one(handle)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                one(handle)
+            lat = {"one_gpu_ms": (time.perf_counter() - t0) * 100.0}
+            ndev = hb.device_count()
+            if ndev >= 2:
+                hkeys = [k.cpu().numpy().view("uint64") for k in keys]
+                try:
+                    hb.set_host_devices(list(range(ndev)))
+                    sh = hb.KeySwitchKeys(hkeys, n, decomp, kms, kcc, sharded_by_modulus=True)
+                finally:
+                    hb.set_host_devices([])
+                hr[:] = r0h
+                one(sh)
+                ref1 = res[:r0.numel() // cts].cpu().numpy().view("uint64")   # device result of ciphertext 0 (computed above)
+                assert (hr[:r0.numel() // cts] == ref1).all(), "sharded key switch differs from the single-GPU result"
+                one(sh)
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    one(sh)
+                lat["sharded_by_modulus_ms"] = (time.perf_counter() - t0) * 100.0
+                lat["shards"] = ndev
+                del sh
+            out["latency_one_switch_host_buffers"] = lat
         hb.pinned_free(ht); hb.pinned_free(hr)
     except hb.HexlB200Error as e:
         out["e2e"] = {"unavailable": str(e)[:120]}

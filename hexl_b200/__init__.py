@@ -119,6 +119,7 @@ _sig("hexl_b200_eltwise_mont_reduce_mod", _int, [_vp, _vp, _vp, _u64, _u64, _int
 _sig("hexl_b200_eltwise_montgomery_form_in", _int, [_vp, _vp, _u64, _u64, _u64, _int, _u64, _vp])
 _sig("hexl_b200_eltwise_montgomery_form_out", _int, [_vp, _vp, _u64, _u64, _int, _u64, _vp])
 _sig("hexl_b200_keys_upload", _int, [C.POINTER(_vp), _vp, _u64, _u64, _u64, _u64])
+_sig("hexl_b200_keys_upload_sharded", _int, [C.POINTER(_vp), _vp, _u64, _u64, _u64, _u64])
 _sig("hexl_b200_keys_release", None, [_vp])
 _sig("hexl_b200_key_switch_resident", _int, [_vp, _vp, _u64, _u64, _u64, _u64, _u64, _vp, _vp, _vp, _u64, _vp])
 
@@ -502,14 +503,17 @@ class KeySwitchKeys:
     named with set_host_devices.  k_switch_keys: list of host or device buffers, each
     key_component_count x key_modulus_size x n words."""
 
-    def __init__(self, k_switch_keys, n, decomp_modulus_size, key_modulus_size, key_component_count):
+    def __init__(self, k_switch_keys, n, decomp_modulus_size, key_modulus_size, key_component_count,
+                 sharded_by_modulus=False):
+        """sharded_by_modulus: split the RNS moduli of ONE key switch over the devices of set_host_devices
+        (hexl_b200_keys_upload_sharded); such a handle serves host buffers only."""
         for k in k_switch_keys[:decomp_modulus_size]:
             _need("k_switch_keys[j]", _buf(k)[1], key_component_count * key_modulus_size * n)
         _need("k_switch_keys", len(k_switch_keys), decomp_modulus_size)
         ptrs = (_vp * len(k_switch_keys))(*[_buf(k)[0] for k in k_switch_keys])
         h = _vp()
-        _check(_lib.hexl_b200_keys_upload(C.byref(h), ptrs, n, decomp_modulus_size, key_modulus_size,
-                                          key_component_count))
+        fn = _lib.hexl_b200_keys_upload_sharded if sharded_by_modulus else _lib.hexl_b200_keys_upload
+        _check(fn(C.byref(h), ptrs, n, decomp_modulus_size, key_modulus_size, key_component_count))
         self._h = h
         self.shape = (n, decomp_modulus_size, key_modulus_size, key_component_count)
 

@@ -59,7 +59,24 @@ struct hexl_b200_keys {
   std::atomic<int> refs{1};
   uint64_t n = 0, decomp = 0, kcc = 0, kms = 0;
   std::map<int, std::vector<uint64_t*>> dev;  // device ordinal -> decomp device buffers
+  // Sharded by RNS modulus (hexl_b200_keys_upload_sharded): shard s owns the RNS moduli [lo, hi) of ONE key switch,
+  // holds only their slices of the keys and a private workspace, on device `device` (a device may carry several shards).
+  struct Shard {
+    int device = 0;
+    uint64_t lo = 0, hi = 0;                 // RNS modulus indices (index decomp = the special prime)
+    std::vector<uint64_t*> keys;             // [j] -> kcc x (hi - lo) x n
+    uint64_t *t_coef = nullptr, *ops = nullptr, *prod = nullptr, *tmp = nullptr, *t_last = nullptr, *res = nullptr,
+             *digits = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t gathered = nullptr, special = nullptr;
+  };
+  std::vector<Shard> shards;
+  std::mutex mu;                             // one sharded switch at a time per handle (the workspaces are per handle)
 };
+
+extern "C" {
+static void free_shards(hexl_b200_keys* k);
+}
 
 namespace {
 
@@ -1521,12 +1538,244 @@ void hexl_b200_keys_release(hexl_b200_keys* k) {
   if (!k || k->refs.fetch_sub(1) != 1) return;
   int prev = -1;
   cudaGetDevice(&prev);
+  free_shards(k);
   for (auto& kv : k->dev)
     if (cudaSetDevice(kv.first) == cudaSuccess)
       for (uint64_t* p : kv.second) cudaFree(p);
   if (prev >= 0) cudaSetDevice(prev);
   cudaGetLastError();
   delete k;
+}
+
+// ---------------------------------------------------------------- one key switch sharded by RNS modulus
+// The reference's loop nest (key-switch-internal.cpp:60-131) makes every output modulus consume every decomposed digit:
+// with the moduli of ONE switch spread over several GPUs that is an all-gather of the digits in coefficient form
+// (decomp x n words) -- the only exchange on this path -- plus a broadcast of the special prime's part
+// (kcc x n words) before the final step (:134-198).  Both ride NVLink as peer copies issued from the producing shard's
+// stream right behind the kernel that produced the data; consumers wait on an event, never on the host.
+//   shard s, moduli [lo, hi):   H2D its digits + its slices of result
+//     A  inverse NTT of its digits                       -> its rows of t_coef on EVERY shard        (all-gather)
+//     B  every digit reduced into its moduli, lazy forward NTTs, multiply-accumulate with ITS key slices -> prod
+//     C  (owner of the special prime) inverse NTT of that part -> t_last on every shard               (broadcast)
+//     D  round, forward NTT, mod-switch, accumulate into its slices of result; D2H
+static int key_switch_sharded(uint64_t* result, const uint64_t* t_target, uint64_t n, uint64_t decomp,
+                              uint64_t key_modulus_size, uint64_t rns, uint64_t kcc, const uint64_t* moduli,
+                              hexl_b200_keys* keys, const uint64_t* modswitch) {
+  std::lock_guard<std::mutex> lk(keys->mu);
+  auto& S = keys->shards;
+  auto ki = [&](uint64_t i) { return i == decomp ? key_modulus_size - 1 : i; };
+  std::vector<hexl_b200_ntt*> h(rns, nullptr);
+  struct Release {
+    std::vector<hexl_b200_ntt*>& v;
+    ~Release() {
+      for (auto* p : v)
+        if (p) hexl_b200_ntt_release(p);
+    }
+  } release{h};
+  for (uint64_t i = 0; i < rns; ++i) {
+    if (moduli[ki(i)] >= (1ull << 61)) return fail(HEXL_B200_ERR_INVALID_ARG, "KeySwitch: Require moduli < 2^61");
+    if (int rc = cached_ntt(&h[i], n, moduli[ki(i)])) return rc;
+  }
+#define SCU(call)                                                 \
+  do {                                                            \
+    cudaError_t e__ = (call);                                     \
+    if (e__ != cudaSuccess) {                                     \
+      for (auto& z : S) {                                         \
+        cudaSetDevice(z.device);                                  \
+        cudaStreamSynchronize(z.stream);                          \
+      }                                                           \
+      return cuda_fail(e__, "sharded KeySwitch: " #call);         \
+    }                                                             \
+  } while (0)
+#define SRC(expr)                                                 \
+  do {                                                            \
+    int rc__ = (expr);                                            \
+    if (rc__) {                                                   \
+      for (auto& z : S) {                                         \
+        cudaSetDevice(z.device);                                  \
+        cudaStreamSynchronize(z.stream);                          \
+      }                                                           \
+      return rc__;                                                \
+    }                                                             \
+  } while (0)
+  int prev = 0;
+  CU(cudaGetDevice(&prev));
+  struct Restore {
+    int d;
+    ~Restore() { cudaSetDevice(d); }
+  } restore{prev};
+  const size_t row = (size_t)decomp * n * sizeof(uint64_t);  // host pitch of result: one key component over all moduli
+  // A: digits in, inverse NTT, all-gather
+  for (auto& z : S) {
+    const uint64_t dhi = std::min<uint64_t>(z.hi, decomp), nd = dhi > z.lo ? dhi - z.lo : 0;
+    SCU(cudaSetDevice(z.device));
+    if (nd) {
+      SCU(cudaMemcpyAsync(z.t_coef + z.lo * n, t_target + z.lo * n, nd * n * 8, cudaMemcpyHostToDevice, z.stream));
+      SCU(cudaMemcpy2DAsync(z.res, nd * n * 8, result + z.lo * n, row, nd * n * 8, kcc, cudaMemcpyHostToDevice, z.stream));
+      SRC(ntt_multi_on_device(false, z.device, h.data() + z.lo, nd, z.t_coef + z.lo * n, z.t_coef + z.lo * n, 1, 1, z.stream));
+      for (auto& p : S)
+        if (&p != &z)
+          SCU(cudaMemcpyPeerAsync(p.t_coef + z.lo * n, p.device, z.t_coef + z.lo * n, z.device, nd * n * 8, z.stream));
+    }
+    SCU(cudaEventRecord(z.gathered, z.stream));
+  }
+  // B: every shard waits for every other shard's digits, then works on its own moduli
+  for (auto& z : S) {
+    SCU(cudaSetDevice(z.device));
+    for (auto& p : S)
+      if (&p != &z) SCU(cudaStreamWaitEvent(z.stream, p.gathered, 0));
+    const uint64_t cnt = z.hi - z.lo, per_mod = decomp * n;
+    for (uint64_t e0 = 0; e0 < cnt; e0 += kParamBlock) {
+      const uint64_t c = std::min<uint64_t>(kParamBlock, cnt - e0);
+      KsModuli mods;
+      for (uint64_t e = 0; e < c; ++e) {
+        const uint64_t q = moduli[ki(z.lo + e0 + e)], mu = nt::multiply_factor(1, 64, q);
+        const Twiddle R = make_twiddle((mu * (0 - q)) % q, q);  // 2^64 mod q
+        mods.m[e] = KsModulus{q, mu, R.w, R.wp, e0 + e};        // key slot = index inside the shard
+      }
+      cudaError_t e = launch_ks_reduce(z.ops + e0 * per_mod, z.t_coef, n, decomp, c, mods, z.stream);
+      if (e != cudaSuccess) SCU(e);
+      SRC(ntt_multi_on_device(true, z.device, h.data() + z.lo + e0, c, z.ops + e0 * per_mod, z.ops + e0 * per_mod, 4, decomp, z.stream));
+      for (uint64_t j0 = 0; j0 < decomp; j0 += kParamBlock) {
+        const uint64_t jc = std::min<uint64_t>(kParamBlock, decomp - j0);
+        KeyPointers kp;
+        for (uint64_t j = 0; j < jc; ++j) kp.p[j] = z.keys[j0 + j];
+        e = launch_ks_mac(z.prod + e0 * kcc * n, z.ops + e0 * per_mod + j0 * n, per_mod, kp, n, jc, kcc, cnt, c, mods, j0 != 0, z.stream);
+        if (e != cudaSuccess) SCU(e);
+      }
+    }
+  }
+  // C: the special prime's part, back to coefficients, to everybody
+  {
+    auto& z = S.back();  // owns RNS index decomp by construction
+    SCU(cudaSetDevice(z.device));
+    NttDeviceTables tl;
+    SRC(device_tables(h[decomp], z.device, &tl, z.stream));
+    cudaError_t e = launch_ntt_inverse(tl, z.t_last, z.prod + (decomp - z.lo) * kcc * n, 2, 2, kcc, z.stream);
+    if (e != cudaSuccess) SCU(e);
+    for (auto& p : S)
+      if (&p != &z) SCU(cudaMemcpyPeerAsync(p.t_last, p.device, z.t_last, z.device, kcc * n * 8, z.stream));
+    SCU(cudaEventRecord(z.special, z.stream));
+  }
+  // D: mod-down and accumulate, results out
+  const uint64_t q_last = moduli[key_modulus_size - 1], mu_last = nt::multiply_factor(1, 64, q_last);
+  for (auto& z : S) {
+    const uint64_t dhi = std::min<uint64_t>(z.hi, decomp), nd = dhi > z.lo ? dhi - z.lo : 0;
+    if (!nd) continue;
+    SCU(cudaSetDevice(z.device));
+    if (&z != &S.back()) SCU(cudaStreamWaitEvent(z.stream, S.back().special, 0));
+    for (uint64_t e0 = 0; e0 < nd; e0 += kParamBlock) {
+      const uint64_t c = std::min<uint64_t>(kParamBlock, nd - e0);
+      KsModuli round_mods, fin_mods;
+      for (uint64_t e = 0; e < c; ++e) {
+        const uint64_t i = z.lo + e0 + e, qi = moduli[i], mu_i = nt::multiply_factor(1, 64, qi);
+        round_mods.m[e] = KsModulus{qi, mu_i, qi - ((q_last >> 1) % qi), 0, 0};
+        const Twiddle ms = make_twiddle(modswitch[i] % qi, qi);
+        fin_mods.m[e] = KsModulus{qi, mu_i, ms.w, ms.wp, 0};
+      }
+      uint64_t* tmp_c = z.tmp + e0 * kcc * n;
+      cudaError_t e = launch_ks_round(tmp_c, z.t_last, n, kcc, q_last, mu_last, c, round_mods, z.stream);
+      if (e != cudaSuccess) SCU(e);
+      SRC(ntt_multi_on_device(true, z.device, h.data() + z.lo + e0, c, tmp_c, tmp_c, 4, kcc, z.stream));
+      e = launch_ks_finish(z.res, z.prod + e0 * kcc * n, tmp_c, n, kcc, nd, e0, c, fin_mods, z.stream);
+      if (e != cudaSuccess) SCU(e);
+    }
+    SCU(cudaMemcpy2DAsync(result + z.lo * n, row, z.res, nd * n * 8, nd * n * 8, kcc, cudaMemcpyDeviceToHost, z.stream));
+  }
+  int rc = 0;
+  for (auto& z : S) {
+    cudaSetDevice(z.device);
+    const cudaError_t e = cudaStreamSynchronize(z.stream);
+    if (e != cudaSuccess && !rc) rc = cuda_fail(e, "sharded KeySwitch");
+  }
+#undef SCU
+#undef SRC
+  return rc;
+}
+
+static void free_shards(hexl_b200_keys* k) {
+  for (auto& z : k->shards) {
+    if (cudaSetDevice(z.device) != cudaSuccess) continue;
+    for (uint64_t* p : z.keys) cudaFree(p);
+    for (uint64_t* p : {z.t_coef, z.ops, z.prod, z.tmp, z.t_last, z.res, z.digits}) cudaFree(p);
+    if (z.stream) cudaStreamDestroy(z.stream);
+    if (z.gathered) cudaEventDestroy(z.gathered);
+    if (z.special) cudaEventDestroy(z.special);
+  }
+  k->shards.clear();
+}
+
+int hexl_b200_keys_upload_sharded(hexl_b200_keys** out, const uint64_t* const* k_switch_keys, uint64_t n,
+                                  uint64_t decomp, uint64_t key_modulus_size, uint64_t kcc) {
+  REQUIRE(out && k_switch_keys, "Require out, k_switch_keys != nullptr");
+  *out = nullptr;
+  REQUIRE(n >= 2 && !(n & (n - 1)), "Require n a power of two");
+  REQUIRE(decomp >= 1 && kcc >= 1 && key_modulus_size >= decomp + 1, "Require decomp, kcc >= 1 and key_modulus_size > decomp");
+  for (uint64_t j = 0; j < decomp; ++j) REQUIRE(k_switch_keys[j] != nullptr, "Require k_switch_keys[j] != nullptr");
+  std::vector<int> devs = host_devices();
+  if (devs.empty()) {
+    int cur = 0;
+    CU(cudaGetDevice(&cur));
+    devs.push_back(cur);
+  }
+  const uint64_t rns = decomp + 1;
+  if (devs.size() > rns) devs.resize(rns);
+  hexl_b200_keys* k = new (std::nothrow) hexl_b200_keys();
+  if (!k) return fail(HEXL_B200_ERR_ALLOC, "out of host memory");
+  k->n = n; k->decomp = decomp; k->kcc = kcc; k->kms = key_modulus_size;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  int rc = 0;
+  const size_t src_pitch = (size_t)key_modulus_size * n * 8;
+  for (size_t si = 0; si < devs.size() && !rc; ++si) {
+    k->shards.emplace_back();
+    auto& z = k->shards.back();
+    z.device = devs[si];
+    z.lo = rns * si / devs.size();
+    z.hi = rns * (si + 1) / devs.size();
+    const uint64_t cnt = z.hi - z.lo, nd = std::min<uint64_t>(z.hi, decomp) > z.lo ? std::min<uint64_t>(z.hi, decomp) - z.lo : 0;
+    cudaError_t e = cudaSetDevice(z.device);
+    for (size_t pj = 0; pj < si && e == cudaSuccess; ++pj)  // NVLink peer mappings in both directions (ignore "already enabled")
+      if (devs[pj] != z.device) {
+        cudaDeviceEnablePeerAccess(devs[pj], 0);
+        cudaGetLastError();
+        cudaSetDevice(devs[pj]);
+        cudaDeviceEnablePeerAccess(z.device, 0);
+        cudaGetLastError();
+        cudaSetDevice(z.device);
+      }
+    auto alloc = [&](uint64_t** p, uint64_t words) {
+      if (e == cudaSuccess) e = cudaMalloc(p, std::max<uint64_t>(words, 1) * 8);
+    };
+    alloc(&z.t_coef, decomp * n);
+    alloc(&z.ops, cnt * decomp * n);
+    alloc(&z.prod, cnt * kcc * n);
+    alloc(&z.tmp, cnt * kcc * n);
+    alloc(&z.t_last, kcc * n);
+    alloc(&z.res, kcc * std::max<uint64_t>(nd, 1) * n);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&z.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&z.gathered, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&z.special, cudaEventDisableTiming);
+    z.keys.assign(decomp, nullptr);
+    for (uint64_t j = 0; j < decomp && e == cudaSuccess; ++j) {
+      alloc(&z.keys[j], kcc * cnt * n);
+      // key slot of RNS index i is i, except the special prime (index decomp) which sits in the last slot
+      if (nd && e == cudaSuccess)
+        e = cudaMemcpy2D(z.keys[j], cnt * n * 8, k_switch_keys[j] + z.lo * n, src_pitch, nd * n * 8, kcc, cudaMemcpyDefault);
+      if (z.hi == rns && e == cudaSuccess)
+        e = cudaMemcpy2D(z.keys[j] + (decomp - z.lo) * n, cnt * n * 8, k_switch_keys[j] + (key_modulus_size - 1) * n, src_pitch,
+                         n * 8, kcc, cudaMemcpyDefault);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) rc = cuda_fail(e, "hexl_b200_keys_upload_sharded");
+  }
+  cudaSetDevice(prev);
+  if (rc) {
+    hexl_b200_keys_release(k);
+    return rc;
+  }
+  *out = k;
+  return 0;
 }
 
 int hexl_b200_key_switch_resident(uint64_t* result, const uint64_t* t_target_iter_ptr, uint64_t n, uint64_t decomp,
@@ -1541,6 +1790,15 @@ int hexl_b200_key_switch_resident(uint64_t* result, const uint64_t* t_target_ite
   if (batch == 0) return 0;
   PtrInfo pi;
   if (int rc = classify_all({result, t_target_iter_ptr}, &pi)) return rc;
+  if (!keys->shards.empty()) {
+    REQUIRE(pi.where == Where::Host, "keys sharded by modulus take host buffers (every shard receives its own slices)");
+    REQUIRE(keys->decomp == decomp, "keys sharded by modulus were uploaded for another decomp_modulus_size");
+    for (uint64_t c = 0; c < batch; ++c)
+      if (int rc = key_switch_sharded(result + c * kcc * decomp * n, t_target_iter_ptr + c * decomp * n, n, decomp,
+                                      key_modulus_size, rns, kcc, moduli, const_cast<hexl_b200_keys*>(keys), modswitch_factors))
+        return rc;
+    return 0;
+  }
   if (pi.where == Where::Host)
     return key_switch_host_batch(result, t_target_iter_ptr, n, decomp, key_modulus_size, rns, kcc, moduli, keys,
                                  modswitch_factors, batch);

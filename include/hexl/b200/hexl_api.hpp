@@ -581,10 +581,12 @@ namespace b200 {
 class KeySwitchKeys {
  public:
   KeySwitchKeys() = default;
+  // sharded_by_modulus: the RNS moduli of ONE switch are spread over the devices of hexl_b200_set_host_devices
+  // (digit all-gather + special-prime broadcast over NVLink); lowers the latency of a single switch on host buffers
   KeySwitchKeys(const uint64_t** k_switch_keys, uint64_t n, uint64_t decomp_modulus_size, uint64_t key_modulus_size,
-                uint64_t key_component_count) {
-    b200_detail::Throw(hexl_b200_keys_upload(&m_keys, k_switch_keys, n, decomp_modulus_size, key_modulus_size,
-                                             key_component_count));
+                uint64_t key_component_count, bool sharded_by_modulus = false) {
+    b200_detail::Throw((sharded_by_modulus ? hexl_b200_keys_upload_sharded : hexl_b200_keys_upload)(
+        &m_keys, k_switch_keys, n, decomp_modulus_size, key_modulus_size, key_component_count));
   }
   ~KeySwitchKeys() { hexl_b200_keys_release(m_keys); }
   KeySwitchKeys(KeySwitchKeys&& o) noexcept : m_keys(o.m_keys) { o.m_keys = nullptr; }

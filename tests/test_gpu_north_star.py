@@ -282,3 +282,39 @@ def test_cold_handle_inside_a_capture_is_refused_and_prepare_fixes_it(hb, checke
     g2.replay()
     torch.cuda.synchronize()
     assert (host(o) == checker.ntt_forward(x, n, q)).all()
+
+
+def test_key_switch_sharded_by_modulus(hb, checker):
+    """hexl_b200_keys_upload_sharded: the RNS moduli of ONE key switch spread over several shards (one per listed
+    device; listing device 0 several times puts several shards on one GPU, so the exchange logic -- digit all-gather,
+    special-prime broadcast, cross-stream events -- runs on any box), bit for bit against the reference; uneven splits,
+    a shard that owns only the special prime, more shards than moduli, key_modulus_size > rns_modulus_size."""
+    ndev = hb.device_count()
+    layouts = [[0], [0, 0], [0, 0, 0], [0] * 9]
+    if ndev >= 2:
+        layouts += [list(range(ndev)), [1, 0, 1]]
+    for n, decomp, extra_slots in ((1 << 12, 7, 0), (1 << 13, 2, 0), (1 << 12, 5, 2)):
+        kcc = 2
+        rns = decomp + 1
+        kms = rns + extra_slots
+        mods = hb.GeneratePrimes(kms, 50, True, n)
+        if extra_slots:   # unused middle slots: the special prime is the LAST modulus (key-switch-internal.cpp:62-63)
+            mods = mods[:decomp] + mods[rns:] + [mods[decomp]]
+        t_target = np.concatenate([uniform_below(30 + j, n, mods[j]) for j in range(decomp)])
+        keys = [np.concatenate([uniform_below(1000 * j + 37 * k + i, n, mods[i]) for k in range(kcc) for i in range(kms)])
+                for j in range(decomp)]
+        result = np.concatenate([uniform_below(5000 + 100 * k + i, n, mods[i]) for k in range(kcc) for i in range(decomp)])
+        modswitch = [hb.InverseMod(mods[-1] % mods[i], mods[i]) for i in range(decomp)]
+        exp = checker.key_switch(result.copy(), t_target, n, decomp, kms, rns, kcc, mods, keys, modswitch)
+        for devices in layouts:
+            try:
+                hb.set_host_devices(devices)
+                handle = hb.KeySwitchKeys(keys, n, decomp, kms, kcc, sharded_by_modulus=True)
+            finally:
+                hb.set_host_devices([])
+            got = np.concatenate([result, result])
+            hb.KeySwitchResident(got, np.concatenate([t_target, t_target]), n, decomp, kms, rns, kcc, mods, handle, modswitch, 2)
+            assert (got[:result.size] == exp).all() and (got[result.size:] == exp).all(), (n, decomp, devices)
+            with pytest.raises(hb.HexlB200Error):   # a sharded handle serves host buffers only
+                hb.KeySwitchResident(dev(result), dev(t_target), n, decomp, kms, rns, kcc, mods, handle, modswitch)
+            del handle

@@ -51,6 +51,12 @@ kh = hb.KeySwitchKeys(keys, n, decomp, kms, kcc)
 hb.KeySwitchResident(torch.cat([res, res]), torch.cat([tt, tt]), n, decomp, kms, rns, kcc, mods, kh, modswitch, 2)
 hres = np.concatenate([res.cpu().numpy().view(np.uint64)] * 2)
 hb.KeySwitchResident(hres, np.concatenate([tt.cpu().numpy().view(np.uint64)] * 2), n, decomp, kms, rns, kcc, mods, kh, modswitch, 2)
+hb.set_host_devices([0, 0])
+khs = hb.KeySwitchKeys(keys, n, decomp, kms, kcc, sharded_by_modulus=True)   # two shards on one GPU: peer copies + events
+hb.set_host_devices([])
+hres2 = np.concatenate([res.cpu().numpy().view(np.uint64)] * 2)
+hb.KeySwitchResident(hres2, np.concatenate([tt.cpu().numpy().view(np.uint64)] * 2), n, decomp, kms, rns, kcc, mods, khs, modswitch, 2)
+assert (hres2 == hres).all()
 ha, hbb = a.cpu().numpy().view(np.uint64), b.cpu().numpy().view(np.uint64)
 ho = np.zeros_like(ha)
 hb.PolyMultiplyMulti(ntts, ho, ha, hbb, 2)
