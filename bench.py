@@ -649,6 +649,24 @@ def run_b200_arm(args):
                    "link_GBps_each_way_per_gpu": link, "clocks": eclk, "numa": numa,
                    "path": "hexl_b200_ntt_forward/inverse with pinned HOST pointers (library stages H2D/kernel/D2H in 32 MiB chunks on 3 streams)",
                    "bound": "PCIe: every transform moves 8N bytes in and 8N bytes out over the host link"}
+            # What the host memory system gives this rank while every other rank asks for the same: 4 threads per rank
+            # copy pinned buffer to pinned buffer at once (numpy releases the GIL).  A staged transform reads 8N host bytes
+            # and writes 8N host bytes per polynomial: `host_traffic_GBps_per_gpu` (the DMA's reads + writes) against
+            # `host_copy_GBps_per_gpu` (the CPUs' reads + writes under the same contention) says whether the e2e rate at
+            # N GPUs is limited by the host's DRAM / fabric rather than by the PCIe link of one GPU.
+            try:
+                nth = 4
+                seg = (n * eb) // nth
+                barrier()
+                t0 = time.perf_counter()
+                th = [threading.Thread(target=lambda i=i: hy.__setitem__(slice(i * seg, (i + 1) * seg), hx[i * seg:(i + 1) * seg]))
+                      for i in range(nth)]
+                [t.start() for t in th]; [t.join() for t in th]
+                dt_copy = max_over_ranks(time.perf_counter() - t0, world)
+                e2e["host_copy_GBps_per_gpu"] = 2 * 8 * seg * nth / dt_copy / 1e9
+                e2e["host_traffic_GBps_per_gpu"] = 2 * link
+            except (RuntimeError, ValueError):
+                pass
             for buf in (hx, hy, hz):
                 hb.pinned_free(buf)
 

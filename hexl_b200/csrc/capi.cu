@@ -12,6 +12,9 @@
 // point returns HEXL_B200_ERR_NO_DEVICE.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -72,6 +75,51 @@ struct hexl_b200_keys {
   };
   std::vector<Shard> shards;
   std::mutex mu;                             // one sharded switch at a time per handle (the workspaces are per handle)
+  // One host thread per shard issues that shard's copies and launches: a switch is ~30 stream operations per shard,
+  // and a single issuing thread (240 operations at ~2.7 us on 8 GPUs) was the whole latency of the first version.
+  struct Pool {
+    std::vector<std::thread> threads;
+    std::mutex m;
+    std::condition_variable cv_go, cv_done;
+    std::function<void(size_t)> job;
+    uint64_t generation = 0;
+    size_t pending = 0;
+    bool stop = false;
+    void start(size_t count) {
+      for (size_t i = 0; i < count; ++i)
+        threads.emplace_back([this, i] {
+          uint64_t seen = 0;
+          for (;;) {
+            std::unique_lock<std::mutex> lk(m);
+            cv_go.wait(lk, [&] { return stop || generation != seen; });
+            if (stop) return;
+            seen = generation;
+            auto fn = job;
+            lk.unlock();
+            fn(i);
+            lk.lock();
+            if (--pending == 0) cv_done.notify_all();
+          }
+        });
+    }
+    void run(std::function<void(size_t)> fn) {
+      std::unique_lock<std::mutex> lk(m);
+      job = std::move(fn);
+      pending = threads.size();
+      ++generation;
+      cv_go.notify_all();
+      cv_done.wait(lk, [&] { return pending == 0; });
+    }
+    void shutdown() {
+      {
+        std::lock_guard<std::mutex> lk(m);
+        stop = true;
+      }
+      cv_go.notify_all();
+      for (auto& t : threads) t.join();
+      threads.clear();
+    }
+  } pool;
 };
 
 extern "C" {
@@ -1576,56 +1624,54 @@ static int key_switch_sharded(uint64_t* result, const uint64_t* t_target, uint64
     if (moduli[ki(i)] >= (1ull << 61)) return fail(HEXL_B200_ERR_INVALID_ARG, "KeySwitch: Require moduli < 2^61");
     if (int rc = cached_ntt(&h[i], n, moduli[ki(i)])) return rc;
   }
-#define SCU(call)                                                 \
-  do {                                                            \
-    cudaError_t e__ = (call);                                     \
-    if (e__ != cudaSuccess) {                                     \
-      for (auto& z : S) {                                         \
-        cudaSetDevice(z.device);                                  \
-        cudaStreamSynchronize(z.stream);                          \
-      }                                                           \
-      return cuda_fail(e__, "sharded KeySwitch: " #call);         \
-    }                                                             \
-  } while (0)
-#define SRC(expr)                                                 \
-  do {                                                            \
-    int rc__ = (expr);                                            \
-    if (rc__) {                                                   \
-      for (auto& z : S) {                                         \
-        cudaSetDevice(z.device);                                  \
-        cudaStreamSynchronize(z.stream);                          \
-      }                                                           \
-      return rc__;                                                \
-    }                                                             \
-  } while (0)
-  int prev = 0;
-  CU(cudaGetDevice(&prev));
-  struct Restore {
-    int d;
-    ~Restore() { cudaSetDevice(d); }
-  } restore{prev};
   const size_t row = (size_t)decomp * n * sizeof(uint64_t);  // host pitch of result: one key component over all moduli
-  // A: digits in, inverse NTT, all-gather
-  for (auto& z : S) {
+  const uint64_t q_last = moduli[key_modulus_size - 1], mu_last = nt::multiply_factor(1, 64, q_last);
+
+  // Every shard's operations are issued by its own host thread; the threads meet at two points, because an event must
+  // have been RECORDED before another stream is told to wait for it.
+  std::atomic<int> first_error{0};
+  std::mutex err_mu;
+  std::string err_text;
+  std::atomic<unsigned> arrived{0};
+  const unsigned nshards = (unsigned)S.size();
+  auto meet = [&](unsigned round) {  // all threads have issued everything of the rounds before `round`
+    arrived.fetch_add(1, std::memory_order_acq_rel);
+    while (arrived.load(std::memory_order_acquire) < round * nshards) std::this_thread::yield();
+  };
+  auto worker = [&](size_t si) {
+    auto& z = S[si];
+    int rc = 0;
+    auto bad = [&](int code) {
+      if (code && !rc) {
+        rc = code;
+        int expected = 0;
+        if (first_error.compare_exchange_strong(expected, code)) {
+          std::lock_guard<std::mutex> g(err_mu);
+          err_text = t_error;  // the message lives in this worker's thread-local slot
+        }
+      }
+      return code != 0;
+    };
+    auto cu = [&](cudaError_t e, const char* what) { return e != cudaSuccess && bad(cuda_fail(e, what)); };
     const uint64_t dhi = std::min<uint64_t>(z.hi, decomp), nd = dhi > z.lo ? dhi - z.lo : 0;
-    SCU(cudaSetDevice(z.device));
-    if (nd) {
-      SCU(cudaMemcpyAsync(z.t_coef + z.lo * n, t_target + z.lo * n, nd * n * 8, cudaMemcpyHostToDevice, z.stream));
-      SCU(cudaMemcpy2DAsync(z.res, nd * n * 8, result + z.lo * n, row, nd * n * 8, kcc, cudaMemcpyHostToDevice, z.stream));
-      SRC(ntt_multi_on_device(false, z.device, h.data() + z.lo, nd, z.t_coef + z.lo * n, z.t_coef + z.lo * n, 1, 1, z.stream));
-      for (auto& p : S)
-        if (&p != &z)
-          SCU(cudaMemcpyPeerAsync(p.t_coef + z.lo * n, p.device, z.t_coef + z.lo * n, z.device, nd * n * 8, z.stream));
-    }
-    SCU(cudaEventRecord(z.gathered, z.stream));
-  }
-  // B: every shard waits for every other shard's digits, then works on its own moduli
-  for (auto& z : S) {
-    SCU(cudaSetDevice(z.device));
-    for (auto& p : S)
-      if (&p != &z) SCU(cudaStreamWaitEvent(z.stream, p.gathered, 0));
     const uint64_t cnt = z.hi - z.lo, per_mod = decomp * n;
-    for (uint64_t e0 = 0; e0 < cnt; e0 += kParamBlock) {
+    const bool last = si + 1 == S.size();
+    cu(cudaSetDevice(z.device), "cudaSetDevice");
+    // A: digits and result slices in, inverse NTT of the digits, all-gather to every peer
+    if (!rc && nd) {
+      cu(cudaMemcpyAsync(z.t_coef + z.lo * n, t_target + z.lo * n, nd * n * 8, cudaMemcpyHostToDevice, z.stream), "H2D digits");
+      if (!rc) cu(cudaMemcpy2DAsync(z.res, nd * n * 8, result + z.lo * n, row, nd * n * 8, kcc, cudaMemcpyHostToDevice, z.stream), "H2D result");
+      if (!rc) bad(ntt_multi_on_device(false, z.device, h.data() + z.lo, nd, z.t_coef + z.lo * n, z.t_coef + z.lo * n, 1, 1, z.stream));
+      for (size_t pi = 0; pi < S.size() && !rc; ++pi)
+        if (pi != si)
+          cu(cudaMemcpyPeerAsync(S[pi].t_coef + z.lo * n, S[pi].device, z.t_coef + z.lo * n, z.device, nd * n * 8, z.stream), "all-gather");
+    }
+    if (!rc) cu(cudaEventRecord(z.gathered, z.stream), "cudaEventRecord");
+    meet(1);
+    // B: wait for everybody's digits; reduce them into my moduli, transform, multiply-accumulate with my key slices
+    for (size_t pi = 0; pi < S.size() && !rc && !first_error.load(); ++pi)
+      if (pi != si) cu(cudaStreamWaitEvent(z.stream, S[pi].gathered, 0), "cudaStreamWaitEvent");
+    for (uint64_t e0 = 0; e0 < cnt && !rc && !first_error.load(); e0 += kParamBlock) {
       const uint64_t c = std::min<uint64_t>(kParamBlock, cnt - e0);
       KsModuli mods;
       for (uint64_t e = 0; e < c; ++e) {
@@ -1633,67 +1679,57 @@ static int key_switch_sharded(uint64_t* result, const uint64_t* t_target, uint64
         const Twiddle R = make_twiddle((mu * (0 - q)) % q, q);  // 2^64 mod q
         mods.m[e] = KsModulus{q, mu, R.w, R.wp, e0 + e};        // key slot = index inside the shard
       }
-      cudaError_t e = launch_ks_reduce(z.ops + e0 * per_mod, z.t_coef, n, decomp, c, mods, z.stream);
-      if (e != cudaSuccess) SCU(e);
-      SRC(ntt_multi_on_device(true, z.device, h.data() + z.lo + e0, c, z.ops + e0 * per_mod, z.ops + e0 * per_mod, 4, decomp, z.stream));
-      for (uint64_t j0 = 0; j0 < decomp; j0 += kParamBlock) {
+      if (cu(launch_ks_reduce(z.ops + e0 * per_mod, z.t_coef, n, decomp, c, mods, z.stream), "ks_reduce")) break;
+      if (bad(ntt_multi_on_device(true, z.device, h.data() + z.lo + e0, c, z.ops + e0 * per_mod, z.ops + e0 * per_mod, 4, decomp, z.stream))) break;
+      for (uint64_t j0 = 0; j0 < decomp && !rc; j0 += kParamBlock) {
         const uint64_t jc = std::min<uint64_t>(kParamBlock, decomp - j0);
         KeyPointers kp;
         for (uint64_t j = 0; j < jc; ++j) kp.p[j] = z.keys[j0 + j];
-        e = launch_ks_mac(z.prod + e0 * kcc * n, z.ops + e0 * per_mod + j0 * n, per_mod, kp, n, jc, kcc, cnt, c, mods, j0 != 0, z.stream);
-        if (e != cudaSuccess) SCU(e);
+        cu(launch_ks_mac(z.prod + e0 * kcc * n, z.ops + e0 * per_mod + j0 * n, per_mod, kp, n, jc, kcc, cnt, c, mods, j0 != 0, z.stream), "ks_mac");
       }
     }
-  }
-  // C: the special prime's part, back to coefficients, to everybody
-  {
-    auto& z = S.back();  // owns RNS index decomp by construction
-    SCU(cudaSetDevice(z.device));
-    NttDeviceTables tl;
-    SRC(device_tables(h[decomp], z.device, &tl, z.stream));
-    cudaError_t e = launch_ntt_inverse(tl, z.t_last, z.prod + (decomp - z.lo) * kcc * n, 2, 2, kcc, z.stream);
-    if (e != cudaSuccess) SCU(e);
-    for (auto& p : S)
-      if (&p != &z) SCU(cudaMemcpyPeerAsync(p.t_last, p.device, z.t_last, z.device, kcc * n * 8, z.stream));
-    SCU(cudaEventRecord(z.special, z.stream));
-  }
-  // D: mod-down and accumulate, results out
-  const uint64_t q_last = moduli[key_modulus_size - 1], mu_last = nt::multiply_factor(1, 64, q_last);
-  for (auto& z : S) {
-    const uint64_t dhi = std::min<uint64_t>(z.hi, decomp), nd = dhi > z.lo ? dhi - z.lo : 0;
-    if (!nd) continue;
-    SCU(cudaSetDevice(z.device));
-    if (&z != &S.back()) SCU(cudaStreamWaitEvent(z.stream, S.back().special, 0));
-    for (uint64_t e0 = 0; e0 < nd; e0 += kParamBlock) {
-      const uint64_t c = std::min<uint64_t>(kParamBlock, nd - e0);
-      KsModuli round_mods, fin_mods;
-      for (uint64_t e = 0; e < c; ++e) {
-        const uint64_t i = z.lo + e0 + e, qi = moduli[i], mu_i = nt::multiply_factor(1, 64, qi);
-        round_mods.m[e] = KsModulus{qi, mu_i, qi - ((q_last >> 1) % qi), 0, 0};
-        const Twiddle ms = make_twiddle(modswitch[i] % qi, qi);
-        fin_mods.m[e] = KsModulus{qi, mu_i, ms.w, ms.wp, 0};
-      }
-      uint64_t* tmp_c = z.tmp + e0 * kcc * n;
-      cudaError_t e = launch_ks_round(tmp_c, z.t_last, n, kcc, q_last, mu_last, c, round_mods, z.stream);
-      if (e != cudaSuccess) SCU(e);
-      SRC(ntt_multi_on_device(true, z.device, h.data() + z.lo + e0, c, tmp_c, tmp_c, 4, kcc, z.stream));
-      e = launch_ks_finish(z.res, z.prod + e0 * kcc * n, tmp_c, n, kcc, nd, e0, c, fin_mods, z.stream);
-      if (e != cudaSuccess) SCU(e);
+    // C: the owner of the special prime brings that part back to coefficients and sends it to everybody
+    if (last && !rc && !first_error.load()) {
+      NttDeviceTables tl;
+      if (!bad(device_tables(h[decomp], z.device, &tl, z.stream)))
+        cu(launch_ntt_inverse(tl, z.t_last, z.prod + (decomp - z.lo) * kcc * n, 2, 2, kcc, z.stream), "special-prime inverse NTT");
+      for (size_t pi = 0; pi < S.size() && !rc; ++pi)
+        if (pi != si) cu(cudaMemcpyPeerAsync(S[pi].t_last, S[pi].device, z.t_last, z.device, kcc * n * 8, z.stream), "broadcast");
+      if (!rc) cu(cudaEventRecord(z.special, z.stream), "cudaEventRecord");
     }
-    SCU(cudaMemcpy2DAsync(result + z.lo * n, row, z.res, nd * n * 8, nd * n * 8, kcc, cudaMemcpyDeviceToHost, z.stream));
+    meet(2);
+    // D: mod-down by the special prime, accumulate into my slices of result, results out
+    if (nd && !rc && !first_error.load()) {
+      if (!last) cu(cudaStreamWaitEvent(z.stream, S.back().special, 0), "cudaStreamWaitEvent");
+      for (uint64_t e0 = 0; e0 < nd && !rc; e0 += kParamBlock) {
+        const uint64_t c = std::min<uint64_t>(kParamBlock, nd - e0);
+        KsModuli round_mods, fin_mods;
+        for (uint64_t e = 0; e < c; ++e) {
+          const uint64_t i = z.lo + e0 + e, qi = moduli[i], mu_i = nt::multiply_factor(1, 64, qi);
+          round_mods.m[e] = KsModulus{qi, mu_i, qi - ((q_last >> 1) % qi), 0, 0};
+          const Twiddle ms = make_twiddle(modswitch[i] % qi, qi);
+          fin_mods.m[e] = KsModulus{qi, mu_i, ms.w, ms.wp, 0};
+        }
+        uint64_t* tmp_c = z.tmp + e0 * kcc * n;
+        if (cu(launch_ks_round(tmp_c, z.t_last, n, kcc, q_last, mu_last, c, round_mods, z.stream), "ks_round")) break;
+        if (bad(ntt_multi_on_device(true, z.device, h.data() + z.lo + e0, c, tmp_c, tmp_c, 4, kcc, z.stream))) break;
+        cu(launch_ks_finish(z.res, z.prod + e0 * kcc * n, tmp_c, n, kcc, nd, e0, c, fin_mods, z.stream), "ks_finish");
+      }
+      if (!rc) cu(cudaMemcpy2DAsync(result + z.lo * n, row, z.res, nd * n * 8, nd * n * 8, kcc, cudaMemcpyDeviceToHost, z.stream), "D2H result");
+    }
+    const cudaError_t e = cudaStreamSynchronize(z.stream);  // always drain: host buffers are in flight
+    if (e != cudaSuccess) cu(e, "cudaStreamSynchronize");
+  };
+  keys->pool.run(worker);
+  if (const int rc = first_error.load()) {
+    t_error = err_text;
+    return rc;
   }
-  int rc = 0;
-  for (auto& z : S) {
-    cudaSetDevice(z.device);
-    const cudaError_t e = cudaStreamSynchronize(z.stream);
-    if (e != cudaSuccess && !rc) rc = cuda_fail(e, "sharded KeySwitch");
-  }
-#undef SCU
-#undef SRC
-  return rc;
+  return 0;
 }
 
 static void free_shards(hexl_b200_keys* k) {
+  k->pool.shutdown();
   for (auto& z : k->shards) {
     if (cudaSetDevice(z.device) != cudaSuccess) continue;
     for (uint64_t* p : z.keys) cudaFree(p);
@@ -1774,6 +1810,7 @@ int hexl_b200_keys_upload_sharded(hexl_b200_keys** out, const uint64_t* const* k
     hexl_b200_keys_release(k);
     return rc;
   }
+  k->pool.start(k->shards.size());
   *out = k;
   return 0;
 }
