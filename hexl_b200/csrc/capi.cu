@@ -74,6 +74,7 @@ struct hexl_b200_keys {
     cudaEvent_t gathered = nullptr, special = nullptr;
   };
   std::vector<Shard> shards;
+  bool p2p = false;                          // every shard can store straight into every other shard's memory
   std::mutex mu;                             // one sharded switch at a time per handle (the workspaces are per handle)
   // One host thread per shard issues that shard's copies and launches: a switch is ~30 stream operations per shard,
   // and a single issuing thread (240 operations at ~2.7 us on 8 GPUs) was the whole latency of the first version.
@@ -721,7 +722,8 @@ int dyadic_on_device(uint64_t* result, const uint64_t* op1, const uint64_t* op2,
 }
 
 int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
-                        const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s);
+                        const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s,
+                        const std::vector<uint64_t*>* mirrors = nullptr);
 
 // key-switch-internal.cpp:25-201 as a short chain of launches on the caller's stream, every
 // step batched over the RNS moduli (multi-modulus NTTs + the glue kernels of seal.cu): about a
@@ -815,13 +817,21 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
 
 
 // `count` handles x `group` polynomials each, device pointers on device `dev`, in blocks of kParamBlock handles
+// mirrors (inverse only): buffers laid out like `result` that receive the final values too (peer memory: NttMulti::mirror)
 int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
-                        const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s) {
+                        const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s,
+                        const std::vector<uint64_t*>* mirrors) {
   const uint64_t n = handles[0]->n;
+  if (mirrors && (forward || mirrors->size() > (size_t)kMaxMirrors))
+    return fail(HEXL_B200_ERR_INVALID_ARG, "mirrored stores: inverse transforms only, at most %d mirrors", kMaxMirrors);
   for (uint64_t first = 0; first < count; first += kParamBlock) {
     const uint64_t cnt = std::min<uint64_t>(kParamBlock, count - first);
     NttMulti multi{};
     multi.group = (unsigned)group;
+    if (mirrors) {
+      multi.mirrors = (unsigned)mirrors->size();
+      for (size_t p = 0; p < mirrors->size(); ++p) multi.mirror[p] = (*mirrors)[p] + first * group * n;
+    }
     uint64_t min_q = ~0ull, max_q = 0;
     for (uint64_t i = 0; i < cnt; ++i) {
       NttDeviceTables t;
@@ -1661,8 +1671,15 @@ static int key_switch_sharded(uint64_t* result, const uint64_t* t_target, uint64
     if (!rc && nd) {
       cu(cudaMemcpyAsync(z.t_coef + z.lo * n, t_target + z.lo * n, nd * n * 8, cudaMemcpyHostToDevice, z.stream), "H2D digits");
       if (!rc) cu(cudaMemcpy2DAsync(z.res, nd * n * 8, result + z.lo * n, row, nd * n * 8, kcc, cudaMemcpyHostToDevice, z.stream), "H2D result");
-      if (!rc) bad(ntt_multi_on_device(false, z.device, h.data() + z.lo, nd, z.t_coef + z.lo * n, z.t_coef + z.lo * n, 1, 1, z.stream));
-      for (size_t pi = 0; pi < S.size() && !rc; ++pi)
+      // the all-gather: the transform's last kernel stores every coefficient into all peers as well (P2P stores over
+      // NVLink, fused into the producing kernel); copy-engine peer copies behind the transform where P2P is unavailable
+      std::vector<uint64_t*> peers;
+      if (keys->p2p)
+        for (size_t pi = 0; pi < S.size(); ++pi)
+          if (pi != si) peers.push_back(S[pi].t_coef + z.lo * n);
+      if (!rc) bad(ntt_multi_on_device(false, z.device, h.data() + z.lo, nd, z.t_coef + z.lo * n, z.t_coef + z.lo * n, 1, 1, z.stream,
+                                       keys->p2p ? &peers : nullptr));
+      for (size_t pi = 0; pi < S.size() && !rc && !keys->p2p; ++pi)
         if (pi != si)
           cu(cudaMemcpyPeerAsync(S[pi].t_coef + z.lo * n, S[pi].device, z.t_coef + z.lo * n, z.device, nd * n * 8, z.stream), "all-gather");
     }
@@ -1690,10 +1707,14 @@ static int key_switch_sharded(uint64_t* result, const uint64_t* t_target, uint64
     }
     // C: the owner of the special prime brings that part back to coefficients and sends it to everybody
     if (last && !rc && !first_error.load()) {
-      NttDeviceTables tl;
-      if (!bad(device_tables(h[decomp], z.device, &tl, z.stream)))
-        cu(launch_ntt_inverse(tl, z.t_last, z.prod + (decomp - z.lo) * kcc * n, 2, 2, kcc, z.stream), "special-prime inverse NTT");
-      for (size_t pi = 0; pi < S.size() && !rc; ++pi)
+      std::vector<uint64_t*> peers;
+      if (keys->p2p)
+        for (size_t pi = 0; pi < S.size(); ++pi)
+          if (pi != si) peers.push_back(S[pi].t_last);
+      hexl_b200_ntt* hl = h[decomp];
+      bad(ntt_multi_on_device(false, z.device, &hl, 1, z.t_last, z.prod + (decomp - z.lo) * kcc * n, 2, kcc, z.stream,
+                              keys->p2p ? &peers : nullptr));
+      for (size_t pi = 0; pi < S.size() && !rc && !keys->p2p; ++pi)
         if (pi != si) cu(cudaMemcpyPeerAsync(S[pi].t_last, S[pi].device, z.t_last, z.device, kcc * n * 8, z.stream), "broadcast");
       if (!rc) cu(cudaEventRecord(z.special, z.stream), "cudaEventRecord");
     }
@@ -1763,6 +1784,7 @@ int hexl_b200_keys_upload_sharded(hexl_b200_keys** out, const uint64_t* const* k
   cudaGetDevice(&prev);
   int rc = 0;
   const size_t src_pitch = (size_t)key_modulus_size * n * 8;
+  bool p2p_all = devs.size() - 1 <= (size_t)kMaxMirrors;
   for (size_t si = 0; si < devs.size() && !rc; ++si) {
     k->shards.emplace_back();
     auto& z = k->shards.back();
@@ -1773,6 +1795,10 @@ int hexl_b200_keys_upload_sharded(hexl_b200_keys** out, const uint64_t* const* k
     cudaError_t e = cudaSetDevice(z.device);
     for (size_t pj = 0; pj < si && e == cudaSuccess; ++pj)  // NVLink peer mappings in both directions (ignore "already enabled")
       if (devs[pj] != z.device) {
+        int ab = 0, ba = 0;
+        cudaDeviceCanAccessPeer(&ab, z.device, devs[pj]);
+        cudaDeviceCanAccessPeer(&ba, devs[pj], z.device);
+        if (!ab || !ba) p2p_all = false;
         cudaDeviceEnablePeerAccess(devs[pj], 0);
         cudaGetLastError();
         cudaSetDevice(devs[pj]);
@@ -1810,6 +1836,8 @@ int hexl_b200_keys_upload_sharded(hexl_b200_keys** out, const uint64_t* const* k
     hexl_b200_keys_release(k);
     return rc;
   }
+  static const bool no_p2p_stores = std::getenv("HEXL_B200_KS_PEER_COPIES") != nullptr;  // force the copy-engine exchange
+  k->p2p = p2p_all && !no_p2p_stores;
   k->pool.start(k->shards.size());
   *out = k;
   return 0;

@@ -73,9 +73,15 @@ cudaError_t launch_ntt_inverse(const NttDeviceTables& t, u64* result, const u64*
 // Multi-modulus launch: polynomial u (of `units` back to back) belongs to entry u / group.
 // At most kParamBlock entries per call; all moduli share the degree 2^log_n.
 constexpr int kParamBlock = 64;
+constexpr int kMaxMirrors = 15;
 struct NttMulti {
   const NttDeviceParams* p[kParamBlock];
   unsigned group;
+  // Inverse transforms only: the kernel that writes the final values also writes them to `mirrors` more buffers at the
+  // same offsets -- peer-mapped memory of other GPUs (P2P stores over NVLink).  This is how the sharded key switch
+  // all-gathers its digits inside the transform that produces them instead of copying afterwards.
+  unsigned mirrors;
+  u64* mirror[kMaxMirrors];
 };
 // max_q = the largest modulus of the call: it selects the butterflies every entry can run
 cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, u64 min_q, u64 max_q, u64* result,

@@ -654,6 +654,13 @@ __device__ __forceinline__ void st_row(void* base, unsigned idx, E v) {
     st_coef<POLICY>(static_cast<u64*>(base) + idx, v);
 }
 
+// Extra destinations of a transform's final stores (see NttMulti::mirror): buffer p receives value v at p[i] + off + idx
+struct MirrorList {
+  u64* const* p;
+  unsigned count;
+  u64 off;
+};
+
 // Forward transform of one row of C = 2^LOGC contiguous coefficients rooted at
 // tree node `base`, by the T = C/16 threads whose index in the row is u.
 template <int MODE, int LOGC, int LD, int ST>
@@ -705,7 +712,7 @@ __device__ __forceinline__ void row_inv_body(void* out, const void* in, typename
                                              u64 base, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod& m,
                                              int out_mf, bool fold, typename Ar<MODE>::Tw inv_n,
                                              typename Ar<MODE>::Tw inv_n_w, bool active,
-                                             typename Ar<MODE>::Tw* cta_stab = nullptr) {
+                                             typename Ar<MODE>::Tw* cta_stab = nullptr, const MirrorList* mir = nullptr) {
   using Cfg = RowCfg<LOGC>;
   using E = typename Ar<MODE>::E;
   using Tw = typename Ar<MODE>::Tw;
@@ -730,6 +737,12 @@ __device__ __forceinline__ void row_inv_body(void* out, const void* in, typename
   if (active) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) st_row<ST, E>(out, reg_index<LB0>(u, e), fold ? inv_out(v[e], m, out_mf) : v[e]);
+    if (mir && fold) {
+      for (unsigned p = 0; p < mir->count; ++p) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) mir->p[p][mir->off + reg_index<LB0>(u, e)] = (u64)inv_out(v[e], m, out_mf);
+      }
+    }
   }
 }
 
@@ -820,7 +833,8 @@ __device__ __forceinline__ void col_stages(typename Ar<MODE>::E (&v)[1 << LOGR],
 template <int MODE, int LOGR, bool FWD, int LD, int ST>
 __device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 off, int log_stride,
                                          const typename Ar<MODE>::Tw* stw, const Mod& m, int out_mf, bool root_fold,
-                                         typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w) {
+                                         typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w,
+                                         const MirrorList* mir = nullptr) {
   using E = typename Ar<MODE>::E;
   constexpr int R = 1 << LOGR;
   E v[R];
@@ -831,6 +845,12 @@ __device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 of
 #pragma unroll
   for (int e = 0; e < R; ++e)
     st_coef<ST>(result + off + ((u64)e << log_stride), final_out ? inv_out(v[e], m, out_mf) : v[e]);
+  if (mir && final_out) {
+    for (unsigned p = 0; p < mir->count; ++p) {
+#pragma unroll
+      for (int e = 0; e < R; ++e) mir->p[p][mir->off + off + ((u64)e << log_stride)] = (u64)inv_out(v[e], m, out_mf);
+    }
+  }
 }
 
 // Sub-blocks of S = 2^log_s contiguous coefficients, each rooted at tree node

@@ -34,9 +34,12 @@ __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE
   if (FWD)
     row_fwd_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C, srow, u, base, P.fwd, m,
                                                out_mf, active);
-  else
+  else {
+    const MirrorList mir{multi.mirror, multi.mirrors, row * Cfg::C};
     row_inv_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C, srow, u, base, P.inv, m,
-                                               out_mf, fold != 0, P.inv_n, P.inv_n_w, active);
+                                               out_mf, fold != 0, P.inv_n, P.inv_n_w, active, nullptr,
+                                               multi.mirrors ? &mir : nullptr);
+  }
 }
 
 template <int MODE, int LOGR, bool FWD>
@@ -62,8 +65,10 @@ __global__ void __launch_bounds__(256)
   const u64 g = g0 + threadIdx.x;
   if (g >= total_cols) return;
   const u64 c = g & ((1ull << log_cols) - 1);
+  const MirrorList mir{multi.mirror, multi.mirrors, 0};
   col_body<MODE, LOGR, FWD, kStream, kStream>(result, operand, (blk << log_s) + c, log_cols, stw, m, out_mf,
-                                              !FWD && fold && log_s == log_n, P.inv_n, P.inv_n_w);
+                                              !FWD && fold && log_s == log_n, P.inv_n, P.inv_n_w,
+                                              (!FWD && multi.mirrors) ? &mir : nullptr);
 }
 
 // N < 16: one thread per polynomial, everything in registers (launch-bound shapes only)
@@ -93,6 +98,9 @@ __global__ void ntt_tiny_multi(u64* result, const u64* operand, const __grid_con
       }
   }
   for (int e = 0; e < n; ++e) result[unit * n + e] = FWD ? fwd_out<kGeneric>(v[e], m, out_mf) : inv_out(v[e], m, out_mf);
+  if (!FWD)
+    for (unsigned p = 0; p < multi.mirrors; ++p)
+      for (int e = 0; e < n; ++e) multi.mirror[p][unit * n + e] = inv_out(v[e], m, out_mf);
 }
 
 template <int MODE, int LOGC>

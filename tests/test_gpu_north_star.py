@@ -318,3 +318,16 @@ def test_key_switch_sharded_by_modulus(hb, checker):
             with pytest.raises(hb.HexlB200Error):   # a sharded handle serves host buffers only
                 hb.KeySwitchResident(dev(result), dev(t_target), n, decomp, kms, rns, kcc, mods, handle, modswitch)
             del handle
+
+
+def test_key_switch_sharded_copy_engine_exchange():
+    """By default the sharded key switch all-gathers its digits with P2P stores from the inverse transform's last kernel
+    (NttMulti::mirror); HEXL_B200_KS_PEER_COPIES=1 selects the copy-engine exchange (cudaMemcpyPeerAsync behind the
+    transform), which is also what runs between GPUs without peer access.  The switch is read once per process."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.abspath(__file__)
+    res = subprocess.run([sys.executable, "-m", "pytest", here, "-m", "gpu", "-x", "-q", "-k", "test_key_switch_sharded_by_modulus"],
+                         env={**os.environ, "HEXL_B200_KS_PEER_COPIES": "1"}, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "1 passed" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
