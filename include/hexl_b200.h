@@ -253,8 +253,9 @@ int hexl_b200_keys_upload(hexl_b200_keys** out, const uint64_t* const* k_switch_
                           uint64_t decomp_modulus_size, uint64_t key_modulus_size, uint64_t key_component_count);
 /* The same keys SHARDED BY RNS MODULUS over the devices of hexl_b200_set_host_devices (one shard per listed device; a
  * device listed twice carries two shards): shard s keeps only the key slices of its moduli.  ONE key switch then runs on
- * all shards at once -- the decomposed digits are all-gathered and the special prime's part is broadcast over NVLink peer
- * copies (the exchange of key-switch-internal.cpp:60-131,134-198) -- which cuts the latency of a single switch;
+ * all shards at once -- the decomposed digits are all-gathered and the special prime's part is broadcast with P2P stores
+ * over NVLink from the kernels that produce them (the exchange of key-switch-internal.cpp:60-131,134-198) -- which cuts
+ * the latency of a single switch;
  * hexl_b200_key_switch_resident takes such a handle with HOST result / t_target buffers. */
 int hexl_b200_keys_upload_sharded(hexl_b200_keys** out, const uint64_t* const* k_switch_keys, uint64_t n,
                                   uint64_t decomp_modulus_size, uint64_t key_modulus_size,

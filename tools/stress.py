@@ -48,7 +48,82 @@ t_end = time.time() + budget
 it = 0
 while time.time() < t_end:
     it += 1
-    kind = rng.choice(["ntt", "ntt", "ntt", "multi", "elt", "elt"])
+    kind = rng.choice(["ntt", "ntt", "ntt", "multi", "elt", "elt", "mont", "ks", "hostcomp"])
+    if kind == "mont":  # Montgomery-form helpers: random odd q < R = 2^r <= 2^62, device / host / unaligned
+        r = int(rng.integers(3, 63))
+        q = int(rng.integers(1 << (r - 2), 1 << r)) | 1
+        if q < 3:
+            q = 3
+        inv = hb.HenselLemma2adicRoot(r, q)
+        n = int(rng.choice([1, 2, 5, 63, 1000, 4097, 1 << 16]))
+        a, b = rand_below(n, q), rand_below(n, q)
+        r2 = (1 << r) * (1 << r) % q
+        on_dev = bool(rng.integers(0, 2))
+        A, B = (dev(a), dev(b)) if on_dev else (a.copy(), b.copy())
+        O = dev(np.zeros(n, dtype=np.uint64)) if on_dev else np.zeros(n, dtype=np.uint64)
+        get = host if on_dev else (lambda t: t)
+        assert (get(hb.EltwiseMontReduceMod(O, A, B, n, q, r, inv)) == chk.mont_reduce_mod(a, b, q, r, inv)).all(), ("mont mul", r, q, n)
+        assert (get(hb.EltwiseMontgomeryFormIn(O, A, r2, n, q, r, inv)) == chk.montgomery_form_in(a, r2, q, r, inv)).all(), ("mont in", r, q, n)
+        assert (get(hb.EltwiseMontgomeryFormOut(O, O, n, q, r, inv)) == a).all(), ("mont out", r, q, n)
+        counts[kind] = counts.get(kind, 0) + 1
+        continue
+    if kind == "ks":  # key switch with resident keys: random shape, batch, host or device buffers, sharded or not
+        logn = int(rng.integers(4, 12))
+        n = 1 << logn
+        decomp = int(rng.integers(1, 6))
+        kms = rns = decomp + 1
+        kcc = int(rng.integers(1, 4))
+        bits = int(rng.choice([33, 45, 50, 58, 60]))
+        mods = hb.GeneratePrimes(kms, max(bits, logn + 3), True, n)
+        keys = [np.concatenate([rand_below(n, mods[i]) for _ in range(kcc) for i in range(kms)]) for _ in range(decomp)]
+        batch = int(rng.integers(1, 4))
+        t = np.concatenate([np.concatenate([rand_below(n, mods[j]) for j in range(decomp)]) for _ in range(batch)])
+        res = np.concatenate([np.concatenate([rand_below(n, mods[i]) for _ in range(kcc) for i in range(decomp)]) for _ in range(batch)])
+        ms = [hb.InverseMod(mods[-1] % mods[i], mods[i]) for i in range(decomp)]
+        rs, ts = kcc * decomp * n, decomp * n
+        exp = np.concatenate([chk.key_switch(res[c * rs:(c + 1) * rs].copy(), t[c * ts:(c + 1) * ts], n, decomp, kms, rns, kcc,
+                                             mods, keys, ms) for c in range(batch)])
+        mode = int(rng.integers(0, 3))
+        if mode == 2:
+            hb.set_host_devices([0] * int(rng.integers(1, 5)))
+            h = hb.KeySwitchKeys(keys, n, decomp, kms, kcc, sharded_by_modulus=True)
+            hb.set_host_devices([])
+        else:
+            h = hb.KeySwitchKeys(keys, n, decomp, kms, kcc)
+        if mode == 0:
+            d = dev(res)
+            hb.KeySwitchResident(d, dev(t), n, decomp, kms, rns, kcc, mods, h, ms, batch)
+            got = host(d)
+        else:
+            got = res.copy()
+            hb.KeySwitchResident(got, t, n, decomp, kms, rns, kcc, mods, h, ms, batch)
+        assert (got == exp).all(), ("ks", logn, decomp, kcc, bits, batch, mode)
+        del h
+        counts[kind] = counts.get(kind, 0) + 1
+        continue
+    if kind == "hostcomp":  # RNS composites on host buffers (chunked staging path)
+        logn = int(rng.integers(2, 14))
+        n = 1 << logn
+        nm = int(rng.integers(1, 5))
+        group = int(rng.integers(1, 4))
+        mods = [prime(int(rng.choice([29, 40, 50, 55, 60])), True, n) for _ in range(nm)]
+        mods = list(dict.fromkeys(mods))
+        nm = len(mods)
+        ntts = [hb.NTT(n, q) for q in mods]
+        sz = n * group
+        a = np.concatenate([rand_below(sz, q) for q in mods])
+        b = np.concatenate([rand_below(sz, q) for q in mods])
+        conv = np.concatenate([chk.ntt_inverse(chk.mult_mod(chk.ntt_forward(a[i * sz:(i + 1) * sz], n, q),
+                                                             chk.ntt_forward(b[i * sz:(i + 1) * sz], n, q), q), n, q)
+                               for i, q in enumerate(mods)])
+        o = np.zeros_like(a)
+        hb.PolyMultiplyMulti(ntts, o, a, b, group)
+        assert (o == conv).all(), ("host polymul", logn, mods, group)
+        fwd = np.concatenate([chk.ntt_forward(a[i * sz:(i + 1) * sz], n, q) for i, q in enumerate(mods)])
+        hb.ComputeForwardMulti(ntts, o, a, 1, 1, batch_per_modulus=group)
+        assert (o == fwd).all(), ("host fwd multi", logn, mods, group)
+        counts[kind] = counts.get(kind, 0) + 1
+        continue
     if kind in ("ntt", "multi"):
         logn = int(rng.integers(1, 18))
         n = 1 << logn
