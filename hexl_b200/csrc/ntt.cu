@@ -177,8 +177,9 @@ cudaError_t launch_pipe_dyn(int log_r, bool fwd, const NttDeviceTables& t, u64* 
 
 // log2(N / 4096) for which the pipelined kernel is used; 0 = none.  HEXL_B200_PIPE: 1 = always (N = 2^14..2^17),
 // 0 = never, unset = where it measured faster than the two-kernel split on B200 (profiles/r2e_pipe_lookahead_sweep.txt,
-// r2d_pipe_vs_split.txt; 2^28 coefficients): forward N = 2^17 (55-bit 3.02 vs 3.20 ms, 29-bit 1.34 vs 1.38) and the
-// 32-bit-word inverse at N >= 2^16 (1.35 vs 1.42, 1.46 vs 1.52).  Elsewhere the split is 2-4 % faster although it
+// r2d_pipe_vs_split.txt, r2m_padded_rows_timings.txt; 2^28 coefficients): forward N = 2^17 (55-bit 2.78 ms, was 3.02 vs
+// 3.20 before the rows were padded; 29-bit 1.34 vs 1.38) and the 32-bit-word inverse at N >= 2^16 (1.35 vs 1.42, 1.46
+// vs 1.52).  Elsewhere the split is 0-3 % faster (N = 2^16, 55-bit: 2.53 / 2.68 vs 2.59 / 2.69 ms) although it
 // moves twice the HBM bytes: the transforms are bound by instruction issue, not by memory.  A batch of fewer
 // polynomials than the pipeline is deep gains nothing from it.
 template <int MODE>

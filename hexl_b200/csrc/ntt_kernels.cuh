@@ -450,6 +450,16 @@ template <typename E>
 __device__ __forceinline__ unsigned swz(unsigned j) {
   return j ^ ((j >> 4) & (sizeof(E) == 8 ? 15u : 31u));
 }
+// 64-bit rows (round 2) are PADDED instead of swizzled: element j lives at j + (j >> 4), one 8-byte pad per 16
+// elements.  Equally conflict-free for every access pattern of the passes (tests/test_kernel_model.py), and -- unlike
+// the XOR -- affine in the register slot: for the slot-e element of a thread, pad(U | e << LB) = pad(U) + pad_slot(e)
+// with a compile-time pad_slot, so the 16 accesses of an exchange are ONE address plus immediate offsets instead of a
+// LOP3/LEA per access (~4 % of the row kernels' instructions).  The 32-bit rows of SMALL mode keep the XOR swizzle.
+__host__ __device__ constexpr unsigned pad_slot(int e, int lb) { return ((unsigned)e << lb) + (((unsigned)e << lb) >> 4); }
+template <typename E>
+__host__ __device__ constexpr unsigned row_elems(int logc) {
+  return (1u << logc) + (sizeof(E) == 8 ? (1u << logc) >> 4 : 0u);
+}
 
 // Coefficient index held in register slot e of thread u when the 4 register
 // bits sit at bit position LB of the row-local index.
@@ -552,14 +562,28 @@ template <int LB_FROM, int LB_TO, typename E>
 __device__ __forceinline__ void smem_exchange(E (&v)[16], E* srow, unsigned u) {
   constexpr bool kWarpLocal = (LB_FROM > LB_TO ? LB_FROM : LB_TO) <= 5;
   if (HEXL_B200_ABLATE & 8) return;
+  if constexpr (sizeof(E) == 8) {
+    const unsigned uf = reg_index<LB_FROM>(u, 0), ut = reg_index<LB_TO>(u, 0);
+    E* wr = srow + (uf + (uf >> 4));
+    const E* rd = srow + (ut + (ut >> 4));
 #pragma unroll
-  for (int e = 0; e < 16; ++e) srow[swz<E>(reg_index<LB_FROM>(u, e))] = v[e];
-  if (kWarpLocal)
-    __syncwarp();
-  else
-    __syncthreads();
+    for (int e = 0; e < 16; ++e) wr[pad_slot(e, LB_FROM)] = v[e];
+    if (kWarpLocal)
+      __syncwarp();
+    else
+      __syncthreads();
 #pragma unroll
-  for (int e = 0; e < 16; ++e) v[e] = srow[swz<E>(reg_index<LB_TO>(u, e))];
+    for (int e = 0; e < 16; ++e) v[e] = rd[pad_slot(e, LB_TO)];
+  } else {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) srow[swz<E>(reg_index<LB_FROM>(u, e))] = v[e];
+    if (kWarpLocal)
+      __syncwarp();
+    else
+      __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = srow[swz<E>(reg_index<LB_TO>(u, e))];
+  }
 }
 
 // Forward passes after pass 0: register bits move down by 4 per pass, clamped at 0.
@@ -616,7 +640,7 @@ struct RowCfg {
   static constexpr int THREADS = T * ROWS;
   static constexpr int PASSES = (LOGC + 3) / 4;
   static constexpr bool TW_TABLES = LOGC >= 8;          // sub-tree twiddles staged in shared memory
-  static constexpr size_t ROW_BYTES = (size_t)C * sizeof(E) + (TW_TABLES ? kRowTwEntries * sizeof(Tw) : 0);
+  static constexpr size_t ROW_BYTES = (size_t)row_elems<E>(LOGC) * sizeof(E) + (TW_TABLES ? kRowTwEntries * sizeof(Tw) : 0);
   static constexpr size_t SMEM = (size_t)ROWS * ROW_BYTES;
   static constexpr int MIN_BLOCKS = THREADS <= 256 ? (MODE == kSmall ? HEXL_B200_ROW_MIN_BLOCKS_SMALL : HEXL_B200_ROW_MIN_BLOCKS)
                                                    : (THREADS == 512 ? HEXL_B200_ROW_MIN_BLOCKS_512 : 1);
@@ -673,7 +697,7 @@ __device__ __forceinline__ void row_fwd_body(void* out, const void* in, typename
   constexpr int LB0 = LOGC - 4;  // pass 0: register bits are the top 4 index bits
   // cta_stab: every row of this CTA has the same root (whole polynomials, N == C): one table
   // filled by all threads of the CTA instead of one per row
-  Tw* stab = cta_stab ? cta_stab : reinterpret_cast<Tw*>(srow + (1 << LOGC));
+  Tw* stab = cta_stab ? cta_stab : reinterpret_cast<Tw*>(srow + row_elems<E>(LOGC));
 #pragma unroll
   for (int e = 0; e < 16; ++e) {
     if (HEXL_B200_ABLATE & 1)
@@ -719,7 +743,7 @@ __device__ __forceinline__ void row_inv_body(void* out, const void* in, typename
   E v[16];
   constexpr int LB0 = LOGC - 4;
   constexpr int LB_IN = LB0 < 4 ? LB0 : 4;  // 16 lanes read one 128-byte line per instruction
-  Tw* stab = cta_stab ? cta_stab : reinterpret_cast<Tw*>(srow + (1 << LOGC));
+  Tw* stab = cta_stab ? cta_stab : reinterpret_cast<Tw*>(srow + row_elems<E>(LOGC));
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = ld_row<LD, E>(in, reg_index<LB_IN>(u, e));
   if constexpr (Cfg::TW_TABLES) {
@@ -761,7 +785,7 @@ __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE
   typename Cfg::Tw* cta_stab = nullptr;  // whole polynomials per row: all rows of the CTA share root node 1
   // (SMALL mode only: +5 % there; in the 64-bit modes the run-time table address costs more than the loads save)
   if (MODE == kSmall && Cfg::ROWS > 1 && Cfg::TW_TABLES && rows_per_poly == 1)
-    cta_stab = reinterpret_cast<typename Cfg::Tw*>(smem + (size_t)Cfg::C * sizeof(typename Cfg::E));
+    cta_stab = reinterpret_cast<typename Cfg::Tw*>(smem + (size_t)row_elems<typename Cfg::E>(LOGC) * sizeof(typename Cfg::E));
   row_fwd_body<MODE, LOGC, kStream, kStream>(
       result + row * Cfg::C, operand + row * Cfg::C,
       reinterpret_cast<typename Cfg::E*>(smem + (size_t)row_local * Cfg::ROW_BYTES), u, base, tw, m, out_mf, active,
@@ -783,7 +807,7 @@ __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE
   typename Cfg::Tw* cta_stab = nullptr;
   // (SMALL mode only: +5 % there; in the 64-bit modes the run-time table address costs more than the loads save)
   if (MODE == kSmall && Cfg::ROWS > 1 && Cfg::TW_TABLES && rows_per_poly == 1)
-    cta_stab = reinterpret_cast<typename Cfg::Tw*>(smem + (size_t)Cfg::C * sizeof(typename Cfg::E));
+    cta_stab = reinterpret_cast<typename Cfg::Tw*>(smem + (size_t)row_elems<typename Cfg::E>(LOGC) * sizeof(typename Cfg::E));
   row_inv_body<MODE, LOGC, kStream, kStream>(
       result + row * Cfg::C, operand + row * Cfg::C,
       reinterpret_cast<typename Cfg::E*>(smem + (size_t)row_local * Cfg::ROW_BYTES), u, base, tw, m, out_mf,

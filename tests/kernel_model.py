@@ -14,8 +14,18 @@ import numpy as np
 
 
 def swz(j, elem_bytes=8):
-    """ntt.cu swz<E>: 64-bit elements XOR a 4-bit field, 32-bit elements (SMALL mode) a 5-bit one"""
-    return j ^ ((j >> 4) & (15 if elem_bytes == 8 else 31))
+    """ntt_kernels.cuh: 64-bit rows are padded (element j at j + (j >> 4): one 8-byte pad per 16 elements, affine in
+    the register slot); the 32-bit rows of SMALL mode XOR a 5-bit field (swz<unsigned>)"""
+    return j + (j >> 4) if elem_bytes == 8 else j ^ ((j >> 4) & 31)
+
+
+def pad_slot(e, lb):
+    """the compile-time part of a padded address: pad(U | e << lb) == pad(U) + pad_slot(e, lb)"""
+    return (e << lb) + ((e << lb) >> 4)
+
+
+def row_elems(c, elem_bytes=8):
+    return c + (c >> 4 if elem_bytes == 8 else 0)
 
 
 def reg_index(u, e, lb):
@@ -78,23 +88,28 @@ class Model:
                         v[e], v[e | (1 << eb)] = f(v[e], v[e | (1 << eb)], w)
 
     def exchange(self, v, u, lb_from, lb_to, c):
-        smem = np.empty(c, dtype=object)
-        writer = np.full(c, -1, dtype=int)
-        written = np.zeros(c, dtype=int)
+        size = row_elems(c)
+        smem = np.empty(size, dtype=object)
+        writer = np.full(size, -1, dtype=int)
+        written = np.zeros(size, dtype=int)
         for e in range(16):
-            idx = swz(reg_index(u, e, lb_from))
+            # the kernel's address form: one per-thread base plus a compile-time slot offset
+            base = swz(reg_index(u, 0, lb_from))
+            idx = base + pad_slot(e, lb_from)
+            assert (idx == swz(reg_index(u, e, lb_from))).all()
             smem[idx] = v[e]
             writer[idx] = u
             np.add.at(written, idx, 1)
-        assert (written == 1).all(), "smem write map is not a permutation"
-        read = np.zeros(c, dtype=int)
+        assert written.max() == 1 and written.sum() == c, "smem write map is not injective"
+        read = np.zeros(size, dtype=int)
         warp_local = True
         for e in range(16):
-            idx = swz(reg_index(u, e, lb_to))
+            idx = swz(reg_index(u, 0, lb_to)) + pad_slot(e, lb_to)
+            assert (written[idx] == 1).all(), "read of a slot nobody wrote"
             v[e] = smem[idx]
             np.add.at(read, idx, 1)
             warp_local &= bool(((writer[idx] >> 5) == (u >> 5)).all())
-        assert (read == 1).all(), "smem read map is not a permutation"
+        assert read.max() == 1 and read.sum() == c, "smem read map is not injective"
         # the kernel uses __syncwarp() instead of __syncthreads() exactly when max(lb) <= 5
         if max(lb_from, lb_to) <= 5:
             assert warp_local, (lb_from, lb_to)

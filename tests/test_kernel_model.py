@@ -82,13 +82,17 @@ def test_shared_memory_maps_conflict_free(logc, elem_bytes):
             assert Model.bank_conflict_degree(u, e, lb, elem_bytes) == 1
 
 
-@pytest.mark.parametrize("elem_bytes", [8, 4])
-def test_swizzle_is_a_bijection_inside_aligned_blocks(elem_bytes):
-    from kernel_model import swz
+def test_swizzle_and_padding_maps():
+    from kernel_model import pad_slot, reg_index, row_elems, swz
     j = np.arange(1 << 14)
-    s = swz(j, elem_bytes)
-    blk = 16 if elem_bytes == 8 else 32
-    assert (np.sort(s) == j).all() and ((s // blk) == (j // blk)).all()
+    s = swz(j, 4)     # 32-bit rows: XOR swizzle, a bijection inside aligned blocks of 32
+    assert (np.sort(s) == j).all() and ((s // 32) == (j // 32)).all()
+    p = swz(j, 8)     # 64-bit rows: padded, strictly increasing, inside the padded row
+    assert (np.diff(p) >= 1).all() and p[-1] < row_elems(1 << 14)
+    u = np.arange(1 << 12)
+    for lb in range(0, 11):   # the affine form the kernel uses
+        for e in range(16):
+            assert (swz(reg_index(u, e, lb), 8) == swz(reg_index(u, 0, lb), 8) + pad_slot(e, lb)).all()
 
 
 @pytest.mark.parametrize("logr", [2, 3, 4, 5])
