@@ -43,6 +43,13 @@ __device__ __forceinline__ u64 csub(u64 x, u64 b) {
   return x >= b ? d : x;
 }
 
+// the same for b < 2^63 (every modulus multiple the NTT butterflies subtract): x - b as a signed number is negative
+// exactly when x < b, so the test is one compare of the high word instead of a 64-bit compare (ISETP + ISETP.EX)
+__device__ __forceinline__ u64 csub_s(u64 x, u64 b) {
+  const u64 d = x - b;
+  return (long long)d < 0 ? x : d;
+}
+
 // [0, k*q) -> [0, q) for k in {1,2,4,8} by conditional subtractions
 template <int K>
 __device__ __forceinline__ u64 reduce_from(u64 x, u64 q) {

@@ -71,6 +71,119 @@ __global__ void __launch_bounds__(256)
                                               (!FWD && multi.mirrors) ? &mir : nullptr);
 }
 
+// The persistent pipelined single kernel of ntt_kernels.cuh (ntt_pipe_fwd / _inv) for RNS batches: the same work
+// queue, producer/consumer counters and L2-resident intermediate; the modulus record of a work item comes from the
+// polynomial it belongs to, and the root sub-tree twiddles are re-staged when a CTA's next item has another modulus.
+template <int MODE, int LOGR, bool FWD>
+__global__ void __launch_bounds__(PipeCfg<LOGR, MODE>::THREADS, PipeCfg<LOGR, MODE>::MIN_BLOCKS)
+    ntt_pipe_multi(u64* result, const u64* operand, const __grid_constant__ NttMulti multi, int out_mf, unsigned units,
+                   unsigned lookahead, unsigned* counter, unsigned* done) {
+  using Cfg = PipeCfg<LOGR, MODE>;
+  using E = typename Ar<MODE>::E;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  E* smem = reinterpret_cast<E*>(smem_raw);
+  __shared__ Twiddle stw[Cfg::R];
+  __shared__ unsigned s_item;
+  constexpr unsigned kProd = FWD ? Cfg::CT : Cfg::R;  // producer items per polynomial (column tiles / rows)
+  const unsigned total = (units + lookahead) * Cfg::SLOTS;
+  unsigned staged = ~0u;                              // modulus entry whose root twiddles sit in stw
+  while (true) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(counter, 1u);
+    __syncthreads();
+    const unsigned item = s_item;
+    if (item >= total) break;
+    const unsigned blk = item / Cfg::SLOTS, j = item % Cfg::SLOTS;
+    const bool producer = j < kProd;
+    if (producer ? blk >= units : blk < lookahead) continue;
+    const unsigned poly = producer ? blk : blk - lookahead;
+    const unsigned entry = poly / multi.group;
+    const NttDeviceParams P = *multi.p[entry];
+    const Mod m = make_mod(P.q, P.mu);
+    const Twiddle* tw = FWD ? P.fwd : P.inv;
+    if (entry != staged) {                            // uniform across the CTA
+      for (int l = threadIdx.x; l < Cfg::R; l += Cfg::THREADS)
+        if (l) stw[l] = ld_tw(tw + l);
+      staged = entry;
+      __syncthreads();
+    }
+    const u64 poly_off = (u64)poly << (Cfg::LOGC + LOGR);
+    if (!producer) {
+      if (threadIdx.x == 0)
+        while (ld_acquire_gpu(done + poly) < kProd) __nanosleep(100);
+      __syncthreads();
+    }
+    if (FWD) {
+      if (producer) {
+        col_body<MODE, LOGR, true, kStream, kViaL2>(result, operand, poly_off + j * Cfg::THREADS + threadIdx.x, Cfg::LOGC,
+                                                    stw, m, out_mf, false, Twiddle{}, Twiddle{});
+      } else {
+        const unsigned r = j - Cfg::CT;
+        u64* row = result + poly_off + (u64)r * Cfg::C;
+        row_fwd_body<MODE, Cfg::LOGC, kViaL2, kStream>(row, row, smem, threadIdx.x, (u64)Cfg::R + r, tw, m, out_mf, true);
+      }
+    } else {
+      if (producer) {
+        const u64 off = poly_off + (u64)j * Cfg::C;
+        row_inv_body<MODE, Cfg::LOGC, kStream, kViaL2>(result + off, operand + off, smem, threadIdx.x, (u64)Cfg::R + j, tw,
+                                                       m, out_mf, false, P.inv_n, P.inv_n_w, true);
+      } else {
+        const MirrorList mir{multi.mirror, multi.mirrors, 0};
+        col_body<MODE, LOGR, false, kViaL2, kStream>(result, result, poly_off + (j - Cfg::R) * Cfg::THREADS + threadIdx.x,
+                                                     Cfg::LOGC, stw, m, out_mf, true, P.inv_n, P.inv_n_w,
+                                                     multi.mirrors ? &mir : nullptr);
+      }
+    }
+    if (producer) {
+      __syncthreads();
+      if (threadIdx.x == 0) red_release_gpu(done + poly, 1u);
+    }
+  }
+}
+
+template <int MODE, int LOGR>
+cudaError_t launch_pipe_multi(bool fwd, const NttMulti& multi, u64* result, const u64* operand, u64 units, int out_mf,
+                              cudaStream_t stream) {
+  using Cfg = PipeCfg<LOGR, MODE>;
+  static const int lookahead_env = env_int("HEXL_B200_PIPE_LOOKAHEAD", 48);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned lookahead = (unsigned)(lookahead_env < 1 ? 1 : lookahead_env);
+  const u64 items = (units + lookahead) * Cfg::SLOTS;
+  const u64 want = (u64)sms * Cfg::MIN_BLOCKS;
+  const unsigned grid = (unsigned)(want < items ? want : items);
+  unsigned* state = nullptr;
+  const size_t bytes = (size_t)(units + 1) * sizeof(unsigned);
+  cudaError_t e = scratch_alloc_async(reinterpret_cast<void**>(&state), bytes, stream);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(state, 0, bytes, stream)) != cudaSuccess) return e;
+  if (fwd) {
+    if ((e = ensure_dynamic_smem<ntt_pipe_multi<MODE, LOGR, true>>(Cfg::SMEM)) != cudaSuccess) return e;
+    ntt_pipe_multi<MODE, LOGR, true><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, out_mf, (unsigned)units,
+                                                                                lookahead, state, state + 1);
+  } else {
+    if ((e = ensure_dynamic_smem<ntt_pipe_multi<MODE, LOGR, false>>(Cfg::SMEM)) != cudaSuccess) return e;
+    ntt_pipe_multi<MODE, LOGR, false><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, out_mf, (unsigned)units,
+                                                                                 lookahead, state, state + 1);
+  }
+  count_launch();
+  e = cudaGetLastError();
+  scratch_free_async(state, stream);
+  return e;
+}
+
+// same rule as the single-modulus launcher (ntt.cu:pipe_log_r): forced by HEXL_B200_PIPE=1, off with =0, else where
+// it measured faster -- the forward transform at N = 2^17
+inline int pipe_multi_log_r(int log_n, u64 units, bool forward) {
+  static const int mode = env_int("HEXL_B200_PIPE", -1);
+  static const int min_batch = env_int("HEXL_B200_PIPE_MIN_BATCH", 64);
+  const int lr = log_n - 12;
+  if (mode == 0 || lr < 2 || lr > 5 || units < (u64)min_batch || units >= (1ull << 31)) return 0;
+  if (mode > 0) return lr;
+  return (forward && log_n == 17) ? lr : 0;
+}
+
 // N < 16: one thread per polynomial, everything in registers (launch-bound shapes only)
 template <bool FWD>
 __global__ void ntt_tiny_multi(u64* result, const u64* operand, const __grid_constant__ NttMulti multi, int log_n,
@@ -168,6 +281,14 @@ cudaError_t launch_col_multi_dyn(int log_r, bool fwd, const NttMulti& multi, int
 template <int MODE>
 cudaError_t multi_impl(bool fwd, const NttMulti& multi, int log_n, u64* result, const u64* operand, int out_mf,
                        u64 units, cudaStream_t stream) {
+  if (const int lr = pipe_multi_log_r(log_n, units, fwd)) {
+    switch (lr) {
+      case 2: return launch_pipe_multi<MODE, 2>(fwd, multi, result, operand, units, out_mf, stream);
+      case 3: return launch_pipe_multi<MODE, 3>(fwd, multi, result, operand, units, out_mf, stream);
+      case 4: return launch_pipe_multi<MODE, 4>(fwd, multi, result, operand, units, out_mf, stream);
+      case 5: return launch_pipe_multi<MODE, 5>(fwd, multi, result, operand, units, out_mf, stream);
+    }
+  }
   const int log_c = pick_row_log(log_n);
   int radices[8];
   const int ncol = plan_col_passes(log_n - log_c, radices);
