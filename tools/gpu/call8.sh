@@ -6,7 +6,7 @@ O=gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/r2g_pytest.txt 2>&1; echo "rc=$?" >> $O/r2g_pytest.txt
 timeout 900 python bench.py --steps 20 --warmup 3 > $O/r2g_bench.json 2> $O/r2g_bench.err; echo "rc=$?" >> $O/r2g_bench.err
 timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/r2g_bench_ref.json 2> $O/r2g_bench_ref.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 200 --csv --log-file $O/r2g_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-composites --no-eltwise > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 400 --csv --log-file $O/r2g_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-composites --no-eltwise > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:ntt_ -s 8 -c 4 -o /tmp/prof_r2g -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-composites --no-eltwise > $O/r2g_ncu.log 2>&1
 ncu -i /tmp/prof_r2g.ncu-rep --page raw --csv > $O/r2g_ncu_raw.csv 2>/dev/null
 for tool in memcheck racecheck; do
