@@ -723,7 +723,7 @@ int dyadic_on_device(uint64_t* result, const uint64_t* op1, const uint64_t* op2,
 
 int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
                         const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s,
-                        const std::vector<uint64_t*>* mirrors = nullptr);
+                        const std::vector<uint64_t*>* mirrors = nullptr, bool gather = false);
 
 // key-switch-internal.cpp:25-201 as a short chain of launches on the caller's stream, every
 // step batched over the RNS moduli (multi-modulus NTTs + the glue kernels of seal.cu): about a
@@ -779,8 +779,9 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
       mods.m[e] = KsModulus{q, mu, R.w, R.wp, slot};
       hs[e] = h[slot];
     }
-    LAUNCH(launch_ks_reduce(ops, t_coef, n, decomp, cnt, mods, s));
-    if (int rc = ntt_multi_on_device(true, dev, hs.data(), cnt, ops, ops, 4, decomp, s)) return rc;
+    // every digit into every modulus of the round (:77-85) happens inside the transform: it reads the digits from
+    // t_coef (L2-resident) and reduces on load, instead of a reduce kernel writing decomp x cnt x n words for it
+    if (int rc = ntt_multi_on_device(true, dev, hs.data(), cnt, ops, t_coef, 4, decomp, s, nullptr, true)) return rc;
     for (uint64_t j0 = 0; j0 < decomp; j0 += kParamBlock) {  // key pointers ride in the kernel parameters
       const uint64_t jc = std::min<uint64_t>(kParamBlock, decomp - j0);
       KeyPointers kp;
@@ -820,8 +821,11 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
 // mirrors (inverse only): buffers laid out like `result` that receive the final values too (peer memory: NttMulti::mirror)
 int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
                         const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s,
-                        const std::vector<uint64_t*>* mirrors) {
+                        const std::vector<uint64_t*>* mirrors, bool gather) {
+  // gather (forward only): `operand` holds ONE group of polynomials; every handle's group reads it and reduces the
+  // values into its own modulus on load (NttMulti::gather)
   const uint64_t n = handles[0]->n;
+  if (gather && !forward) return fail(HEXL_B200_ERR_INVALID_ARG, "gather: forward transforms only");
   if (mirrors && (forward || mirrors->size() > (size_t)kMaxMirrors))
     return fail(HEXL_B200_ERR_INVALID_ARG, "mirrored stores: inverse transforms only, at most %d mirrors", kMaxMirrors);
   for (uint64_t first = 0; first < count; first += kParamBlock) {
@@ -841,8 +845,9 @@ int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, ui
       max_q = std::max(max_q, t.q);
     }
     const uint64_t off = first * group * n;
-    cudaError_t e = launch_ntt_multi(forward, multi, handles[0]->log_n, min_q, max_q, result + off, operand + off,
-                                     out_mf, cnt * group, s);
+    multi.gather = gather ? (unsigned)group : 0u;
+    cudaError_t e = launch_ntt_multi(forward, multi, handles[0]->log_n, min_q, max_q, result + off,
+                                     gather ? operand : operand + off, out_mf, cnt * group, s);
     if (e != cudaSuccess) return cuda_fail(e, "multi-modulus NTT launch");
   }
   return 0;
@@ -1696,8 +1701,7 @@ static int key_switch_sharded(uint64_t* result, const uint64_t* t_target, uint64
         const Twiddle R = make_twiddle((mu * (0 - q)) % q, q);  // 2^64 mod q
         mods.m[e] = KsModulus{q, mu, R.w, R.wp, e0 + e};        // key slot = index inside the shard
       }
-      if (cu(launch_ks_reduce(z.ops + e0 * per_mod, z.t_coef, n, decomp, c, mods, z.stream), "ks_reduce")) break;
-      if (bad(ntt_multi_on_device(true, z.device, h.data() + z.lo + e0, c, z.ops + e0 * per_mod, z.ops + e0 * per_mod, 4, decomp, z.stream))) break;
+      if (bad(ntt_multi_on_device(true, z.device, h.data() + z.lo + e0, c, z.ops + e0 * per_mod, z.t_coef, 4, decomp, z.stream, nullptr, true))) break;
       for (uint64_t j0 = 0; j0 < decomp && !rc; j0 += kParamBlock) {
         const uint64_t jc = std::min<uint64_t>(kParamBlock, decomp - j0);
         KeyPointers kp;

@@ -82,6 +82,11 @@ struct NttMulti {
   // all-gathers its digits inside the transform that produces them instead of copying afterwards.
   unsigned mirrors;
   u64* mirror[kMaxMirrors];
+  // Forward transforms only: when non-zero, unit u READS polynomial (u % gather) of `operand` (result still goes to
+  // unit u) and every value is first reduced into its own modulus (any 64-bit value -> [0, q)).  This is KeySwitch's
+  // "every digit into every modulus" step (key-switch-internal.cpp:77-85) folded into the transform that consumes it:
+  // the digits are read from L2 instead of a decomp x rns x n intermediate being written to and read back from HBM.
+  unsigned gather;
 };
 // max_q = the largest modulus of the call: it selects the butterflies every entry can run
 cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, u64 min_q, u64 max_q, u64* result,

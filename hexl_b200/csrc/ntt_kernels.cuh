@@ -308,6 +308,10 @@ __device__ __forceinline__ u64 barrett_lazy3_bigq(u64 x, const Mod& m) {
   return join(t0, mad_lo(Q, m.n1, t1));
 }
 
+// any 64-bit value -> [0, q) (Barrett with floor(2^64/q), then one conditional subtraction; q < 2^63)
+__device__ __forceinline__ u64 reduce_any(u64 x, const Mod& m) { return csub_s(barrett_lazy(x, m), m.q); }
+__device__ __forceinline__ unsigned reduce_any(unsigned x, const Mod& m) { return x % (unsigned)m.q; }
+
 // ----------------------------------------------------------------- butterflies
 template <int MODE, typename TW>
 __device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, const TW& w, const Mod& m) {
@@ -692,7 +696,8 @@ struct MirrorList {
 template <int MODE, int LOGC, int LD, int ST>
 __device__ __forceinline__ void row_fwd_body(void* out, const void* in, typename Ar<MODE>::E* srow, unsigned u,
                                              u64 base, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod& m,
-                                             int out_mf, bool active, typename Ar<MODE>::Tw* cta_stab = nullptr) {
+                                             int out_mf, bool active, typename Ar<MODE>::Tw* cta_stab = nullptr,
+                                             bool reduce_in = false) {
   using E = typename Ar<MODE>::E;
   using Tw = typename Ar<MODE>::Tw;
   E v[16];
@@ -706,6 +711,12 @@ __device__ __forceinline__ void row_fwd_body(void* out, const void* in, typename
       v[e] = (E)((u * 16 + e) * 0x9E3779B97F4A7C15ull + base) & (E)(m.q - 1);
     else
       v[e] = ld_row<LD, E>(in, reg_index<LB0>(u, e));
+  }
+  if constexpr (LD != kSmemRow && sizeof(E) == 8) {
+    if (reduce_in) {  // NttMulti::gather: the input is a value of ANOTHER modulus
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = reduce_any(v[e], m);
+    }
   }
   if constexpr (RowCfg<LOGC>::TW_TABLES) {
     if (!(HEXL_B200_ABLATE & 16)) {
@@ -860,12 +871,18 @@ template <int MODE, int LOGR, bool FWD, int LD, int ST>
 __device__ __forceinline__ void col_body(u64* result, const u64* operand, u64 off, int log_stride,
                                          const typename Ar<MODE>::Tw* stw, const Mod& m, int out_mf, bool root_fold,
                                          typename Ar<MODE>::Tw inv_n, typename Ar<MODE>::Tw inv_n_w,
-                                         const MirrorList* mir = nullptr) {
+                                         const MirrorList* mir = nullptr, bool reduce_in = false) {
   using E = typename Ar<MODE>::E;
   constexpr int R = 1 << LOGR;
   E v[R];
 #pragma unroll
   for (int e = 0; e < R; ++e) v[e] = (E)ld_coef<LD>(operand + off + ((u64)e << log_stride));
+  if constexpr (FWD && sizeof(E) == 8) {
+    if (reduce_in) {
+#pragma unroll
+      for (int e = 0; e < R; ++e) v[e] = reduce_any(v[e], m);
+    }
+  }
   col_stages<MODE, LOGR, FWD>(v, stw, m, root_fold, inv_n, inv_n_w);
   const bool final_out = !FWD && root_fold;
 #pragma unroll

@@ -20,7 +20,7 @@ __device__ __forceinline__ NttDeviceParams load_params(const NttMulti& multi, u6
 template <int MODE, int LOGC, bool FWD>
 __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE>::MIN_BLOCKS)
     ntt_row_multi(u64* result, const u64* operand, const __grid_constant__ NttMulti multi, u64 total_rows,
-                  unsigned rows_per_poly, int out_mf, int fold) {
+                  unsigned rows_per_poly, int out_mf, int fold, unsigned gather) {
   using Cfg = RowCfg<LOGC, MODE>;
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned row_local = threadIdx.x / Cfg::T, u = threadIdx.x % Cfg::T;
@@ -31,10 +31,13 @@ __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE
   const Mod m = make_mod(P.q, P.mu);
   const u64 base = (u64)rows_per_poly + (row % rows_per_poly);
   typename Cfg::E* srow = reinterpret_cast<typename Cfg::E*>(smem + (size_t)row_local * Cfg::ROW_BYTES);
-  if (FWD)
-    row_fwd_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C, srow, u, base, P.fwd, m,
-                                               out_mf, active);
-  else {
+  if (FWD) {
+    // gather (first kernel of a forward transform only): read the same row of polynomial (poly % gather)
+    const u64 poly = row / rows_per_poly;
+    const u64 src_row = gather ? (poly % gather) * rows_per_poly + row % rows_per_poly : row;
+    row_fwd_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + src_row * Cfg::C, srow, u, base, P.fwd, m,
+                                               out_mf, active, nullptr, gather != 0);
+  } else {
     const MirrorList mir{multi.mirror, multi.mirrors, row * Cfg::C};
     row_inv_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C, srow, u, base, P.inv, m,
                                                out_mf, fold != 0, P.inv_n, P.inv_n_w, active, nullptr,
@@ -45,7 +48,7 @@ __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE
 template <int MODE, int LOGR, bool FWD>
 __global__ void __launch_bounds__(256)
     ntt_col_multi(u64* result, const u64* operand, const __grid_constant__ NttMulti multi, int log_n, int log_s,
-                  u64 total_cols, int out_mf, int fold) {
+                  u64 total_cols, int out_mf, int fold, unsigned gather) {
   constexpr int R = 1 << LOGR;
   __shared__ Twiddle stw[R];
   const int log_cols = log_s - LOGR;
@@ -66,9 +69,13 @@ __global__ void __launch_bounds__(256)
   if (g >= total_cols) return;
   const u64 c = g & ((1ull << log_cols) - 1);
   const MirrorList mir{multi.mirror, multi.mirrors, 0};
-  col_body<MODE, LOGR, FWD, kStream, kStream>(result, operand, (blk << log_s) + c, log_cols, stw, m, out_mf,
+  // gather (first column pass of a forward transform: log_s == log_n, one sub-block per polynomial): the source is
+  // polynomial (poly % gather); col_body adds the same offset to both pointers, so the operand base is shifted
+  const u64 poly = blk >> (log_n - log_s);
+  const u64* src = (FWD && gather) ? operand + (((poly % gather) - poly) << log_n) : operand;
+  col_body<MODE, LOGR, FWD, kStream, kStream>(result, src, (blk << log_s) + c, log_cols, stw, m, out_mf,
                                               !FWD && fold && log_s == log_n, P.inv_n, P.inv_n_w,
-                                              (!FWD && multi.mirrors) ? &mir : nullptr);
+                                              (!FWD && multi.mirrors) ? &mir : nullptr, FWD && gather != 0);
 }
 
 // The persistent pipelined single kernel of ntt_kernels.cuh (ntt_pipe_fwd / _inv) for RNS batches: the same work
@@ -194,7 +201,11 @@ __global__ void ntt_tiny_multi(u64* result, const u64* operand, const __grid_con
   const Mod m = make_mod(P.q, P.mu);
   const int n = 1 << log_n;
   u64 v[8];
-  for (int e = 0; e < n; ++e) v[e] = operand[unit * n + e];
+  const u64 src_unit = (FWD && multi.gather) ? unit % multi.gather : unit;
+  for (int e = 0; e < n; ++e) {
+    v[e] = operand[src_unit * n + e];
+    if (FWD && multi.gather) v[e] %= P.q;
+  }
   for (int k = 0; k < log_n; ++k) {
     const int s = FWD ? k : log_n - 1 - k;  // stage: 2^s groups, span t
     const int t = n >> (s + 1);
@@ -218,7 +229,7 @@ __global__ void ntt_tiny_multi(u64* result, const u64* operand, const __grid_con
 
 template <int MODE, int LOGC>
 cudaError_t launch_row_multi(bool fwd, const NttMulti& multi, int log_n, u64* result, const u64* operand, u64 units,
-                             int out_mf, int fold, cudaStream_t stream) {
+                             int out_mf, int fold, cudaStream_t stream, unsigned gather = 0) {
   using Cfg = RowCfg<LOGC, MODE>;
   const unsigned rows_per_poly = 1u << (log_n - LOGC);
   const u64 total_rows = units * rows_per_poly;
@@ -226,11 +237,11 @@ cudaError_t launch_row_multi(bool fwd, const NttMulti& multi, int log_n, u64* re
   if (fwd) {
     if (cudaError_t e = ensure_dynamic_smem<ntt_row_multi<MODE, LOGC, true>>(Cfg::SMEM)) return e;
     ntt_row_multi<MODE, LOGC, true><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, total_rows,
-                                                                               rows_per_poly, out_mf, fold);
+                                                                               rows_per_poly, out_mf, fold, gather);
   } else {
     if (cudaError_t e = ensure_dynamic_smem<ntt_row_multi<MODE, LOGC, false>>(Cfg::SMEM)) return e;
     ntt_row_multi<MODE, LOGC, false><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, total_rows,
-                                                                                rows_per_poly, out_mf, fold);
+                                                                                rows_per_poly, out_mf, fold, 0u);
   }
   count_launch();
   return cudaGetLastError();
@@ -238,10 +249,11 @@ cudaError_t launch_row_multi(bool fwd, const NttMulti& multi, int log_n, u64* re
 
 template <int MODE>
 cudaError_t launch_row_multi_dyn(int log_c, bool fwd, const NttMulti& multi, int log_n, u64* result,
-                                 const u64* operand, u64 units, int out_mf, int fold, cudaStream_t stream) {
+                                 const u64* operand, u64 units, int out_mf, int fold, cudaStream_t stream,
+                                 unsigned gather = 0) {
   switch (log_c) {
 #define ROW_CASE(L) \
-  case L: return launch_row_multi<MODE, L>(fwd, multi, log_n, result, operand, units, out_mf, fold, stream);
+  case L: return launch_row_multi<MODE, L>(fwd, multi, log_n, result, operand, units, out_mf, fold, stream, gather);
     ROW_CASE(4) ROW_CASE(5) ROW_CASE(6) ROW_CASE(7) ROW_CASE(8) ROW_CASE(9) ROW_CASE(10)
     ROW_CASE(11) ROW_CASE(12) ROW_CASE(13) ROW_CASE(14)
 #undef ROW_CASE
@@ -251,27 +263,28 @@ cudaError_t launch_row_multi_dyn(int log_c, bool fwd, const NttMulti& multi, int
 
 template <int MODE, int LOGR>
 cudaError_t launch_col_multi(bool fwd, const NttMulti& multi, int log_n, u64* result, const u64* operand, u64 units,
-                             int log_s, int out_mf, int fold, cudaStream_t stream) {
+                             int log_s, int out_mf, int fold, cudaStream_t stream, unsigned gather = 0) {
   const u64 total_cols = (units << log_n) >> LOGR;
   const u64 cols_per_block = 1ull << (log_s - LOGR);
   const unsigned threads = (unsigned)(cols_per_block < 256 ? cols_per_block : 256);
   const unsigned grid = (unsigned)((total_cols + threads - 1) / threads);
   if (fwd)
     ntt_col_multi<MODE, LOGR, true><<<grid, threads, 0, stream>>>(result, operand, multi, log_n, log_s, total_cols,
-                                                                  out_mf, fold);
+                                                                  out_mf, fold, gather);
   else
     ntt_col_multi<MODE, LOGR, false><<<grid, threads, 0, stream>>>(result, operand, multi, log_n, log_s, total_cols,
-                                                                   out_mf, fold);
+                                                                   out_mf, fold, 0u);
   count_launch();
   return cudaGetLastError();
 }
 
 template <int MODE>
 cudaError_t launch_col_multi_dyn(int log_r, bool fwd, const NttMulti& multi, int log_n, u64* result,
-                                 const u64* operand, u64 units, int log_s, int out_mf, int fold, cudaStream_t stream) {
+                                 const u64* operand, u64 units, int log_s, int out_mf, int fold, cudaStream_t stream,
+                                 unsigned gather = 0) {
   switch (log_r) {
 #define COL_CASE(L) \
-  case L: return launch_col_multi<MODE, L>(fwd, multi, log_n, result, operand, units, log_s, out_mf, fold, stream);
+  case L: return launch_col_multi<MODE, L>(fwd, multi, log_n, result, operand, units, log_s, out_mf, fold, stream, gather);
     COL_CASE(1) COL_CASE(2) COL_CASE(3) COL_CASE(4) COL_CASE(5)
 #undef COL_CASE
   }
@@ -281,7 +294,8 @@ cudaError_t launch_col_multi_dyn(int log_r, bool fwd, const NttMulti& multi, int
 template <int MODE>
 cudaError_t multi_impl(bool fwd, const NttMulti& multi, int log_n, u64* result, const u64* operand, int out_mf,
                        u64 units, cudaStream_t stream) {
-  if (const int lr = pipe_multi_log_r(log_n, units, fwd)) {
+  const unsigned gather = fwd ? multi.gather : 0u;
+  if (const int lr = gather ? 0 : pipe_multi_log_r(log_n, units, fwd)) {
     switch (lr) {
       case 2: return launch_pipe_multi<MODE, 2>(fwd, multi, result, operand, units, out_mf, stream);
       case 3: return launch_pipe_multi<MODE, 3>(fwd, multi, result, operand, units, out_mf, stream);
@@ -296,12 +310,13 @@ cudaError_t multi_impl(bool fwd, const NttMulti& multi, int log_n, u64* result, 
     const u64* src = operand;
     int log_s = log_n;
     for (int p = 0; p < ncol; ++p) {
-      cudaError_t e = launch_col_multi_dyn<MODE>(radices[p], true, multi, log_n, result, src, units, log_s, out_mf, 0, stream);
+      cudaError_t e = launch_col_multi_dyn<MODE>(radices[p], true, multi, log_n, result, src, units, log_s, out_mf, 0, stream,
+                                                 p == 0 ? gather : 0u);
       if (e != cudaSuccess) return e;
       log_s -= radices[p];
       src = result;
     }
-    return launch_row_multi_dyn<MODE>(log_c, true, multi, log_n, result, src, units, out_mf, 0, stream);
+    return launch_row_multi_dyn<MODE>(log_c, true, multi, log_n, result, src, units, out_mf, 0, stream, ncol == 0 ? gather : 0u);
   }
   cudaError_t e = launch_row_multi_dyn<MODE>(log_c, false, multi, log_n, result, operand, units, out_mf, ncol == 0, stream);
   if (e != cudaSuccess) return e;
