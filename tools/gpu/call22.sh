@@ -1,0 +1,16 @@
+#!/bin/bash
+# final pass on the final code
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+O=gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q > $O/r2r_pytest.txt 2>&1; echo "rc=$?" >> $O/r2r_pytest.txt
+timeout 900 python bench.py --steps 20 --warmup 3 > $O/r2r_bench.json 2> $O/r2r_bench.err; echo "rc=$?" >> $O/r2r_bench.err
+timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $O/r2r_bench_ref.json 2> $O/r2r_bench_ref.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 0 -c 400 --csv --log-file $O/r2r_launches.csv python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-composites --no-eltwise > /dev/null 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ntt_ -s 8 -c 4 -o /tmp/prof_r2r -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-composites --no-eltwise > $O/r2r_ncu.log 2>&1
+ncu -i /tmp/prof_r2r.ncu-rep --page raw --csv > $O/r2r_ncu_raw.csv 2>/dev/null
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py > $O/r2r_san_memcheck.log 2>&1
+timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_run.py > $O/r2r_san_racecheck.log 2>&1
+timeout 300 python tools/stress.py 180 23 > $O/r2r_stress.log 2>&1
+python __graft_entry__.py smoke > $O/r2r_smoke.log 2>&1
+tail -n 3 $O/r2r_pytest.txt; head -c 300 $O/r2r_bench.json; echo; tail -n 2 $O/r2r_bench.err; tail -n 2 $O/r2r_san_*.log; tail -n 1 $O/r2r_stress.log; tail -n 1 $O/r2r_smoke.log
