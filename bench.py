@@ -323,11 +323,14 @@ def c4_leg(args, hb, torch, rank, world, gen, sync, peak, cpu_ok):
     fn = lambda: hb.PolyMultiplyMulti(ntts, r, a, b, group)
     fn(); fn()
     ms = max_over_ranks(gpu_time_ms(torch, fn, 5, sync), world)
-    out = {"workload": f"FwdNTT x2 -> EltwiseMultMod -> InvNTT, N=2^17, {nmod} x 60-bit moduli, {group} polynomials per modulus",
+    fused = os.environ.get("HEXL_B200_NO_PRODUCT_FUSION", "0") in ("", "0")
+    bpp = 56 if fused else 72  # bytes per coefficient of one product: 2 x 16 (transforms) + 16 + 8 (inverse, multiplied on load)
+    out = {"workload": (f"FwdNTT x2 -> InvNTT multiplying on load (EltwiseMultMod folded in), " if fused else
+                        f"FwdNTT x2 -> EltwiseMultMod -> InvNTT, ") + f"N=2^17, {nmod} x 60-bit moduli, {group} polynomials per modulus",
            "value": nmod * group / (ms * 1e-3), "unit": "residue products/s", "ms_per_call": ms, "scaling": "strong",
            "moduli_per_rank": [nmod * (k + 1) // world - nmod * k // world for k in range(world)],
-           "algorithmic_bytes_per_product": 72 * n,
-           "hbm_GBps_per_gpu": 72.0 * n * len(mods) * group / (ms * 1e-3) / 1e9,
+           "algorithmic_bytes_per_product": bpp * n,
+           "hbm_GBps_per_gpu": float(bpp) * n * len(mods) * group / (ms * 1e-3) / 1e9,
            "limit": "integer-multiply pipe of the three transforms (no inter-GPU traffic: each rank owns whole moduli)"}
     out["frac_of_hbm_peak"] = out["hbm_GBps_per_gpu"] / peak
     # end to end: pageable-free pinned host buffers through the chunked staging path of the same call

@@ -381,6 +381,7 @@ int check_bounds(const u64* p, u64 n, u64 bound, const PtrInfo& pi, const char* 
 
 // --------------------------------------------------------------- NTT tables
 int floor_log2(uint64_t x) { return 63 - __builtin_clzll(x); }
+DyadicModulus dyadic_modulus(uint64_t q);
 
 bool check_ntt_arguments(uint64_t degree, uint64_t q, const char** why) {
   // NTT::CheckArguments, hexl/ntt/ntt-internal.cpp:171-186
@@ -479,7 +480,8 @@ int device_tables(hexl_b200_ntt* h, int dev, NttDeviceTables* out, cudaStream_t 
       CU_T(cudaMemcpy(d.fwd32, f32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
       CU_T(cudaMemcpy(d.inv32, i32.data(), h->n * sizeof(Twiddle32), cudaMemcpyHostToDevice));
     }
-    NttDeviceParams hp{d.fwd, d.inv, h->q, nt::multiply_factor(1, 64, h->q), h->inv_n, h->inv_n_w};
+    const DyadicModulus pm = dyadic_modulus(h->q);
+    NttDeviceParams hp{d.fwd, d.inv, h->q, nt::multiply_factor(1, 64, h->q), h->inv_n, h->inv_n_w, pm.mu, pm.shift};
     CU_T(cudaMalloc(&d.params, sizeof(NttDeviceParams)));
     CU_T(cudaMemcpy(d.params, &hp, sizeof(NttDeviceParams), cudaMemcpyHostToDevice));
     // A pageable-source cudaMemcpy may return once the data sits in the driver's staging buffer; the
@@ -723,7 +725,8 @@ int dyadic_on_device(uint64_t* result, const uint64_t* op1, const uint64_t* op2,
 
 int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
                         const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s,
-                        const std::vector<uint64_t*>* mirrors = nullptr, bool gather = false);
+                        const std::vector<uint64_t*>* mirrors = nullptr, bool gather = false,
+                        const uint64_t* mul = nullptr);
 
 // key-switch-internal.cpp:25-201 as a short chain of launches on the caller's stream, every
 // step batched over the RNS moduli (multi-modulus NTTs + the glue kernels of seal.cu): about a
@@ -821,11 +824,13 @@ int key_switch_on_device(int dev, uint64_t* result, const uint64_t* t_target, ui
 // mirrors (inverse only): buffers laid out like `result` that receive the final values too (peer memory: NttMulti::mirror)
 int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
                         const uint64_t* operand, int out_mf, uint64_t group, cudaStream_t s,
-                        const std::vector<uint64_t*>* mirrors, bool gather) {
+                        const std::vector<uint64_t*>* mirrors, bool gather, const uint64_t* mul) {
+  // mul (inverse only): laid out like `operand`; the transform multiplies by it on load (NttMulti::mul)
   // gather (forward only): `operand` holds ONE group of polynomials; every handle's group reads it and reduces the
   // values into its own modulus on load (NttMulti::gather)
   const uint64_t n = handles[0]->n;
   if (gather && !forward) return fail(HEXL_B200_ERR_INVALID_ARG, "gather: forward transforms only");
+  if (mul && forward) return fail(HEXL_B200_ERR_INVALID_ARG, "multiply on load: inverse transforms only");
   if (mirrors && (forward || mirrors->size() > (size_t)kMaxMirrors))
     return fail(HEXL_B200_ERR_INVALID_ARG, "mirrored stores: inverse transforms only, at most %d mirrors", kMaxMirrors);
   for (uint64_t first = 0; first < count; first += kParamBlock) {
@@ -846,6 +851,7 @@ int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, ui
     }
     const uint64_t off = first * group * n;
     multi.gather = gather ? (unsigned)group : 0u;
+    multi.mul = mul ? mul + off : nullptr;
     cudaError_t e = launch_ntt_multi(forward, multi, handles[0]->log_n, min_q, max_q, result + off,
                                      gather ? operand : operand + off, out_mf, cnt * group, s);
     if (e != cudaSuccess) return cuda_fail(e, "multi-modulus NTT launch");
@@ -856,6 +862,11 @@ int ntt_multi_on_device(bool forward, int dev, hexl_b200_ntt* const* handles, ui
 // Host-pointer RNS jobs (count moduli x per_mod elements, modulus m owns [m*per_mod, (m+1)*per_mod)) go through
 // the same chunked, multi-stream, multi-device staging as the single-modulus calls: a chunk [off, off + elems)
 // is cut at the modulus boundaries it contains and every piece is launched under its own modulus.
+// HEXL_B200_NO_PRODUCT_FUSION=1: the unfused chain (lazy transforms, MultMod kernel, inverse), kept for measurement
+static bool product_fusion() {
+  static const bool on = !(getenv("HEXL_B200_NO_PRODUCT_FUSION") && atoi(getenv("HEXL_B200_NO_PRODUCT_FUSION")) != 0);
+  return on;
+}
 enum class RnsJob { NttFwd, NttInv, Mult, Add, Sub, PolyMul };
 EltParams mult_params(uint64_t q, int in_mf) {
   EltParams p{};
@@ -894,6 +905,16 @@ struct RnsSegLaunch {
         case RnsJob::PolyMul: {  // staged buffers: r == a (slot buffer 0), b = slot buffer 1; all in place
           u64* fa = r + o;
           u64* fb = const_cast<u64*>(b) + o;
+          if (product_fusion() && moduli[m] >= (1ull << 30)) {  // (below 2^30 the 32-bit-word transforms win)
+            if ((e = launch_ntt_forward(t[m], fa, a + o, 1, 1, cnt / n, s)) != cudaSuccess) return e;
+            if ((e = launch_ntt_forward(t[m], fb, fb, 1, 1, cnt / n, s)) != cudaSuccess) return e;
+            NttMulti multi{};
+            multi.p[0] = t[m].dparams;
+            multi.group = (unsigned)(cnt / n);
+            multi.mul = fb;
+            e = launch_ntt_multi(false, multi, t[m].log_n, moduli[m], moduli[m], fa, fa, 1, cnt / n, s);
+            break;
+          }
           if ((e = launch_ntt_forward(t[m], fa, a + o, 1, 4, cnt / n, s)) != cudaSuccess) return e;
           if ((e = launch_ntt_forward(t[m], fb, fb, 1, 4, cnt / n, s)) != cudaSuccess) return e;
           EltParams p = mult_params(moduli[m], 4);
@@ -1390,7 +1411,7 @@ int hexl_b200_eltwise_sub_mod_multi(uint64_t* result, const uint64_t* operand1, 
   return rns_eltwise_entry(kRnsSub, result, operand1, operand2, n_per_modulus, moduli, num_moduli, 1, stream);
 }
 
-// FwdNTT(a), FwdNTT(b) (lazy outputs), point-wise product, InvNTT: all moduli per launch
+// FwdNTT(a), FwdNTT(b), point-wise product, InvNTT: all moduli per launch
 static int poly_multiply_on_device(int dev, hexl_b200_ntt* const* handles, uint64_t count, uint64_t* result,
                                    const uint64_t* a, const uint64_t* b, uint64_t group, cudaStream_t s) {
   const uint64_t n = handles[0]->n, total = count * group * n;
@@ -1400,6 +1421,13 @@ static int poly_multiply_on_device(int dev, hexl_b200_ntt* const* handles, uint6
   if (int rc = ws.get(&fb, total)) return rc;
   std::vector<uint64_t> moduli(count);
   for (uint64_t i = 0; i < count; ++i) moduli[i] = handles[i]->q;
+  if (product_fusion()) {
+    // canonical transforms, then ONE inverse transform that multiplies on load: no MultMod kernel, and the product
+    // never travels to HBM and back (dyadic-multiply-internal.cpp:17-73 folded into the transform that consumes it)
+    if (int rc = ntt_multi_on_device(true, dev, handles, count, result, a, 1, group, s)) return rc;
+    if (int rc = ntt_multi_on_device(true, dev, handles, count, fb, b, 1, group, s)) return rc;
+    return ntt_multi_on_device(false, dev, handles, count, result, result, 1, group, s, nullptr, false, fb);
+  }
   if (int rc = ntt_multi_on_device(true, dev, handles, count, result, a, 4, group, s)) return rc;
   if (int rc = ntt_multi_on_device(true, dev, handles, count, fb, b, 4, group, s)) return rc;
   if (int rc = rns_eltwise_on_device(kRnsMult, result, result, fb, group * n, moduli.data(), count, 4, s)) return rc;

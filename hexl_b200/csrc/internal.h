@@ -47,6 +47,11 @@ struct NttDeviceParams {
   const Twiddle* inv;
   u64 q, mu;
   Twiddle inv_n, inv_n_w;
+  // generalised-Barrett constants of the point-wise product (eltwise-mult-mod-internal.hpp:52-99, alpha = 62,
+  // beta = -2): prod_shift = bits(q) - 2, prod_mu = floor(2^(prod_shift + 64) / q).  Used by the inverse transform
+  // that multiplies on load (NttMulti::mul).
+  u64 prod_mu;
+  int prod_shift;
 };
 struct NttDeviceTables {
   const Twiddle* fwd;
@@ -87,6 +92,12 @@ struct NttMulti {
   // "every digit into every modulus" step (key-switch-internal.cpp:77-85) folded into the transform that consumes it:
   // the digits are read from L2 instead of a decomp x rns x n intermediate being written to and read back from HBM.
   unsigned gather;
+  // Inverse transforms only: when non-null, the kernel that reads `operand` multiplies every value by the value at the
+  // same offset of `mul` (both canonical, i.e. forward outputs with output_mod_factor 1) before its first butterfly:
+  // InvNTT(a (.) b) in one pass over the data -- the FwdNTT -> MultMod -> InvNTT chain of
+  // dyadic-multiply-internal.cpp:17-73 / the product pipelines of the callers without the MultMod kernel and without
+  // the product's round trip through HBM (24 B per coefficient less).
+  const u64* mul;
 };
 // max_q = the largest modulus of the call: it selects the butterflies every entry can run
 cudaError_t launch_ntt_multi(bool forward, const NttMulti& multi, int log_n, u64 min_q, u64 max_q, u64* result,

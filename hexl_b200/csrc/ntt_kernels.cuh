@@ -312,6 +312,36 @@ __device__ __forceinline__ u64 barrett_lazy3_bigq(u64 x, const Mod& m) {
 __device__ __forceinline__ u64 reduce_any(u64 x, const Mod& m) { return csub_s(barrett_lazy(x, m), m.q); }
 __device__ __forceinline__ unsigned reduce_any(unsigned x, const Mod& m) { return x % (unsigned)m.q; }
 
+// Second operand of an inverse transform that multiplies on load (NttMulti::mul): row pointer + the generalised-Barrett
+// constants of NttDeviceParams.
+struct ProdIn {
+  const u64* b;
+  u64 mu;
+  int shift;
+};
+// x*y mod q for canonical x, y, lazily (eltwise-mult-mod-internal.hpp:52-99 without the final conditional
+// subtraction): U = x*y (four wide products, both halves), c1 = floor(U / 2^shift), Q = floor(c1*mu / 2^64),
+// U - Q*q.  Exact Q -> [0,2q) (GENERIC inverse inputs); Q low by up to two more (FAST / WIDE) -> [0,4q), inside what
+// those modes' first inverse stage accepts.
+template <int MODE>
+__device__ __forceinline__ u64 prod_lazy(u64 x, u64 y, const Mod& m, u64 pmu, int shift) {
+  unsigned x0, x1, y0, y1, q0, q1, t0, t1;
+  split(x, x0, x1);
+  split(y, y0, y1);
+  const u64 t = mul_wide(x0, y0);
+  const u64 uu = mad_wide(x0, y1, (u64)hi32(t));
+  const u64 vv = mad_wide(x1, y0, (u64)lo32(uu));
+  const u64 hi = mad_wide(x1, y1, (u64)hi32(uu) + (u64)hi32(vv));
+  const u64 lo = join(lo32(t), lo32(vv));
+  const u64 c1 = shift ? ((lo >> shift) | (hi << (64 - shift))) : lo;
+  const u64 Q = (MODE == kFast || MODE == kWide) ? mulhi_approx(c1, pmu) : mulhi(c1, pmu);
+  split(Q, q0, q1);
+  split(mad_wide(q0, m.n0, lo), t0, t1);
+  t1 = mad_lo(q0, m.n1, t1);
+  t1 = mad_lo(q1, m.n0, t1);
+  return join(t0, t1);
+}
+
 // ----------------------------------------------------------------- butterflies
 template <int MODE, typename TW>
 __device__ __forceinline__ void fwd_bfly(u64& X, u64& Y, const TW& w, const Mod& m) {
@@ -749,7 +779,8 @@ __device__ __forceinline__ void row_inv_body(void* out, const void* in, typename
                                              u64 base, const typename Ar<MODE>::Tw* __restrict__ tw, const Mod& m,
                                              int out_mf, bool fold, typename Ar<MODE>::Tw inv_n,
                                              typename Ar<MODE>::Tw inv_n_w, bool active,
-                                             typename Ar<MODE>::Tw* cta_stab = nullptr, const MirrorList* mir = nullptr) {
+                                             typename Ar<MODE>::Tw* cta_stab = nullptr, const MirrorList* mir = nullptr,
+                                             const ProdIn* prod = nullptr) {
   using Cfg = RowCfg<LOGC>;
   using E = typename Ar<MODE>::E;
   using Tw = typename Ar<MODE>::Tw;
@@ -759,6 +790,13 @@ __device__ __forceinline__ void row_inv_body(void* out, const void* in, typename
   Tw* stab = cta_stab ? cta_stab : reinterpret_cast<Tw*>(srow + row_elems<E>(LOGC));
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = ld_row<LD, E>(in, reg_index<LB_IN>(u, e));
+  if constexpr (LD != kSmemRow && sizeof(E) == 8) {
+    if (prod) {  // NttMulti::mul: the transform of a point-wise product, multiplied on load
+#pragma unroll
+      for (int e = 0; e < 16; ++e)
+        v[e] = prod_lazy<MODE>(v[e], ld_coef<LD>(prod->b + reg_index<LB_IN>(u, e)), m, prod->mu, prod->shift);
+    }
+  }
   if constexpr (Cfg::TW_TABLES) {
     if (cta_stab)
       load_row_twiddles<LOGC>(stab, threadIdx.x, blockDim.x, base, tw);

@@ -17,7 +17,8 @@ __device__ __forceinline__ NttDeviceParams load_params(const NttMulti& multi, u6
 
 // rows of one CTA must share a modulus: ROWS divides rows_per_poly * group or the launcher
 // falls back to one row per ... (see launch_row_multi: grid is built per polynomial row set)
-template <int MODE, int LOGC, bool FWD>
+// MUL (inverse only): multiply by multi.mul on load -- a separate instantiation, so the plain inverse keeps its code
+template <int MODE, int LOGC, bool FWD, bool MUL = false>
 __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE>::MIN_BLOCKS)
     ntt_row_multi(u64* result, const u64* operand, const __grid_constant__ NttMulti multi, u64 total_rows,
                   unsigned rows_per_poly, int out_mf, int fold, unsigned gather) {
@@ -39,9 +40,10 @@ __global__ void __launch_bounds__(RowCfg<LOGC, MODE>::THREADS, RowCfg<LOGC, MODE
                                                out_mf, active, nullptr, gather != 0);
   } else {
     const MirrorList mir{multi.mirror, multi.mirrors, row * Cfg::C};
+    const ProdIn prod{MUL ? multi.mul + row * Cfg::C : nullptr, P.prod_mu, P.prod_shift};
     row_inv_body<MODE, LOGC, kStream, kStream>(result + row * Cfg::C, operand + row * Cfg::C, srow, u, base, P.inv, m,
                                                out_mf, fold != 0, P.inv_n, P.inv_n_w, active, nullptr,
-                                               multi.mirrors ? &mir : nullptr);
+                                               multi.mirrors ? &mir : nullptr, MUL ? &prod : nullptr);
   }
 }
 
@@ -205,6 +207,7 @@ __global__ void ntt_tiny_multi(u64* result, const u64* operand, const __grid_con
   for (int e = 0; e < n; ++e) {
     v[e] = operand[src_unit * n + e];
     if (FWD && multi.gather) v[e] %= P.q;
+    if (!FWD && multi.mul) v[e] = prod_lazy<kGeneric>(v[e], multi.mul[unit * n + e], m, P.prod_mu, P.prod_shift);
   }
   for (int k = 0; k < log_n; ++k) {
     const int s = FWD ? k : log_n - 1 - k;  // stage: 2^s groups, span t
@@ -238,6 +241,10 @@ cudaError_t launch_row_multi(bool fwd, const NttMulti& multi, int log_n, u64* re
     if (cudaError_t e = ensure_dynamic_smem<ntt_row_multi<MODE, LOGC, true>>(Cfg::SMEM)) return e;
     ntt_row_multi<MODE, LOGC, true><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, total_rows,
                                                                                rows_per_poly, out_mf, fold, gather);
+  } else if (multi.mul) {
+    if (cudaError_t e = ensure_dynamic_smem<ntt_row_multi<MODE, LOGC, false, true>>(Cfg::SMEM)) return e;
+    ntt_row_multi<MODE, LOGC, false, true><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, total_rows,
+                                                                                      rows_per_poly, out_mf, fold, 0u);
   } else {
     if (cudaError_t e = ensure_dynamic_smem<ntt_row_multi<MODE, LOGC, false>>(Cfg::SMEM)) return e;
     ntt_row_multi<MODE, LOGC, false><<<grid, Cfg::THREADS, Cfg::SMEM, stream>>>(result, operand, multi, total_rows,
@@ -295,7 +302,7 @@ template <int MODE>
 cudaError_t multi_impl(bool fwd, const NttMulti& multi, int log_n, u64* result, const u64* operand, int out_mf,
                        u64 units, cudaStream_t stream) {
   const unsigned gather = fwd ? multi.gather : 0u;
-  if (const int lr = gather ? 0 : pipe_multi_log_r(log_n, units, fwd)) {
+  if (const int lr = (gather || multi.mul) ? 0 : pipe_multi_log_r(log_n, units, fwd)) {
     switch (lr) {
       case 2: return launch_pipe_multi<MODE, 2>(fwd, multi, result, operand, units, out_mf, stream);
       case 3: return launch_pipe_multi<MODE, 3>(fwd, multi, result, operand, units, out_mf, stream);

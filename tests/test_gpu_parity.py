@@ -282,6 +282,55 @@ def test_rns_product_pipeline_matches_oracle(hb, checker, logn, group, nmods):
     assert (h == conv).all()
 
 
+@pytest.mark.parametrize("logn", [1, 3, 4, 9, 12, 13, 16])
+@pytest.mark.parametrize("bits", [[50, 55], [60, 60], [33, 60], [20, 50]])
+def test_product_multiplied_on_load_extremes(hb, checker, logn, bits):
+    """The inverse transform that multiplies on load (NttMulti::mul; dyadic-multiply-internal.cpp:17-73 folded into the
+    transform): all three 64-bit butterfly classes ([50,55] FAST, [60,60] and mixed WIDE), every kernel shape (one thread
+    per polynomial, single row kernel, row + column kernels), operands at 0 / 1 / q-1 / random, against the checker."""
+    n = 1 << logn
+    mods = []
+    for bb in bits:
+        mods += [q for q in hb.GeneratePrimes(2, max(bb, logn + 2), True, n) if q not in mods][:1]
+    ntts = [hb.NTT(n, q) for q in mods]
+    group = 3
+    sz = n * group
+    parts_a, parts_b = [], []
+    for i, q in enumerate(mods):
+        a = uniform_below(40 + i, sz, q)
+        b = uniform_below(50 + i, sz, q)
+        a[:n] = q - 1                      # first polynomial: all q-1 times all q-1
+        b[:n] = q - 1
+        b[n:n + n // 2] = 0                # second: zeros, ones and q-1 mixed with random values
+        b[n + n // 2:2 * n] = 1
+        a[n:2 * n:2] = q - 1
+        parts_a.append(a)
+        parts_b.append(b)
+    a, b = np.concatenate(parts_a), np.concatenate(parts_b)
+    conv = np.concatenate([
+        checker.ntt_inverse(checker.mult_mod(checker.ntt_forward(a[i * sz:(i + 1) * sz], n, q),
+                                             checker.ntt_forward(b[i * sz:(i + 1) * sz], n, q), q), n, q)
+        for i, q in enumerate(mods)])
+    o = dev(np.zeros_like(a))
+    hb.PolyMultiplyMulti(ntts, o, dev(a), dev(b), group)
+    assert (host(o) == conv).all()
+    h = np.zeros_like(a)
+    hb.PolyMultiplyMulti(ntts, h, a, b, group)      # host pointers: per-modulus segments
+    assert (h == conv).all()
+
+
+def test_unfused_product_chain_still_matches():
+    """HEXL_B200_NO_PRODUCT_FUSION=1 selects the chain of lazy transforms + MultMod kernel + inverse (read once per process)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.abspath(__file__)
+    res = subprocess.run([sys.executable, "-m", "pytest", here, "-m", "gpu", "-x", "-q", "-k",
+                          "test_rns_product_pipeline_matches_oracle or test_product_multiplied_on_load_extremes"],
+                         env={**os.environ, "HEXL_B200_NO_PRODUCT_FUSION": "1"}, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and " passed" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
 def test_multi_modulus_more_than_one_parameter_block(hb, checker):
     n, group = 256, 2
     mods = hb.GeneratePrimes(70, 40, True, n)
