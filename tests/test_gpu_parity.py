@@ -291,7 +291,7 @@ def test_product_multiplied_on_load_extremes(hb, checker, logn, bits):
     n = 1 << logn
     mods = []
     for bb in bits:
-        mods += [q for q in hb.GeneratePrimes(2, max(bb, logn + 2), True, n) if q not in mods][:1]
+        mods += [q for q in hb.GeneratePrimes(2, max(bb, logn + 6), True, n) if q not in mods][:1]
     ntts = [hb.NTT(n, q) for q in mods]
     group = 3
     sz = n * group
