@@ -140,13 +140,13 @@ def bind_to_gpu_numa(local: int):
 
 
 def source_hash() -> str:
-    """sha256 over the kernel sources: profiles/traffic.json is only believed when it was captured on this code"""
+    """sha256 over the sources of the transform kernels the roofline is about (hexl_b200_ntt_forward / _inverse):
+    profiles/traffic.json is only believed when it was captured on this code"""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "hexl_b200", "csrc")
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh", ".h", ".cpp")):
-            h.update(open(os.path.join(d, name), "rb").read())
+    for name in ("internal.h", "modarith.cuh", "ntt.cu", "ntt_kernels.cuh"):
+        h.update(open(os.path.join(d, name), "rb").read())
     return h.hexdigest()[:16]
 
 

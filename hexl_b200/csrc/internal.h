@@ -134,9 +134,6 @@ struct KsModulus {
 struct KsModuli {
   KsModulus m[kParamBlock];
 };
-// ops[e][j][l] = t_coef[j][l] mod q_e                     (e < count, j < decomp, l < n)
-cudaError_t launch_ks_reduce(u64* ops, const u64* t_coef, u64 n, u64 decomp, u64 count, const KsModuli& mods,
-                             cudaStream_t stream);
 // prod[e][k][l] (+)= sum_{j < jcount} ops[e][j][l] * keys[j][k][c_e][l]  mod q_e ; ops_stride = elements between e's
 cudaError_t launch_ks_mac(u64* prod, const u64* ops, u64 ops_stride, const KeyPointers& keys, u64 n, u64 jcount,
                           u64 kcc, u64 key_modulus_size, u64 count, const KsModuli& mods, int accumulate,

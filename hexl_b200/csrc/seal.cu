@@ -121,19 +121,7 @@ __global__ void __launch_bounds__(kThreads)
 // ---- KeySwitch glue (key-switch-internal.cpp:60-198), every kernel batched over the RNS
 // moduli of one parameter block; layouts are [modulus][component or digit][n].
 
-// :77-85: every digit, in coefficient form, reduced into modulus e.  The reference copies
-// when q_j <= q_e (the value is already < q_e) and reduces otherwise; one Barrett does both.
-__global__ void __launch_bounds__(kThreads)
-    ks_reduce_kernel(u64* ops, const u64* t_coef, u64 per_mod /* decomp*n */, u64 count,
-                     const __grid_constant__ KsModuli mods) {
-  const u64 total = per_mod * count;
-  const u64 stride = (u64)gridDim.x * kThreads;
-  for (u64 g = (u64)blockIdx.x * kThreads + threadIdx.x; g < total; g += stride) {
-    const u64 e = g / per_mod, src = g - e * per_mod;
-    const KsModulus& md = mods.m[e];
-    ops[g] = csub(barrett64_lazy(t_coef[src], md.q, md.mu), md.q);
-  }
-}
+// (:77-85, every digit reduced into every modulus, is folded into the forward transform: NttMulti::gather)
 
 // :93-130: lazy 128-bit multiply-accumulate of the digits with the switching keys, one
 // Shoup(hi, 2^64 mod q) + Barrett(lo) at the end, two conditional subtractions.
@@ -234,18 +222,6 @@ cudaError_t launch_rns_eltwise(int op, u64* result, const u64* a, const u64* b, 
     rns_eltwise_kernel<2><<<(unsigned)blocks, kThreads, 0, stream>>>(result, a, b, per_mod, count, op, in_mf, mods);
   else
     rns_eltwise_kernel<1><<<(unsigned)blocks, kThreads, 0, stream>>>(result, a, b, per_mod, count, op, in_mf, mods);
-  count_launch();
-  return cudaGetLastError();
-}
-
-cudaError_t launch_ks_reduce(u64* ops, const u64* t_coef, u64 n, u64 decomp, u64 count, const KsModuli& mods,
-                             cudaStream_t stream) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  u64 blocks = blocks_for(decomp * n * count);
-  if (blocks > (u64)sms * 16) blocks = (u64)sms * 16;
-  ks_reduce_kernel<<<(unsigned)blocks, kThreads, 0, stream>>>(ops, t_coef, decomp * n, count, mods);
   count_launch();
   return cudaGetLastError();
 }
