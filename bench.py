@@ -86,6 +86,16 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def wait_first(self, work=None, timeout=3.0):
+        """Keep the GPU busy (work()) until nvidia-smi has printed its first sample, so that the tool's start-up
+        (NVML initialisation, a few hundred ms) lands in the warm-up and only its periodic queries in the timed region."""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            if work:
+                work()
+            else:
+                time.sleep(0.01)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
@@ -532,6 +542,7 @@ def run_b200_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_first(lambda: (step(), torch.cuda.synchronize()))
     launches0 = hb.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -637,6 +648,7 @@ def run_b200_arm(args):
             esampler = ClockSampler(local)
             if rank == 0:
                 esampler.start()
+                esampler.wait_first()
             barrier()
             t0 = time.perf_counter()
             for _ in range(esteps):
