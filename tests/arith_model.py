@@ -130,3 +130,67 @@ def simulate_inverse_pass_bounds(K, nslots=16):
             nb[e | (1 << s)] = K_FAST_PROD
         b = nb
     return b, worst, ok
+
+
+# ---- SMALL mode (q < 2^30): one 32-bit word per value (ntt_kernels.cuh:mul_tw32 / csub32)
+def csub32(x, c):
+    return min(x, (x - c) & M32)
+
+
+def mul_tw32(x, w, q):
+    wp = (w << 32) // q
+    Q = (x * wp) >> 32
+    return (x * w + Q * ((1 << 32) - q)) & M32
+
+
+# ---- Montgomery reduction with R = 2^r (eltwise.cu:MontParams::redc): hi:lo < q*R -> T / R mod q
+def redc(hi, lo, q, r):
+    mask = (1 << r) - 1
+    ninv = (-pow(q, -1, 1 << r)) % (1 << r)
+    mm = ((lo & mask) * ninv) & mask
+    mq = mm * q
+    t_lo = (lo + (mq & M64)) & M64
+    t_hi = (hi + (mq >> 64) + (1 if t_lo < lo else 0)) & M64
+    s = ((t_hi << (64 - r)) | (t_lo >> r)) & M64
+    return csub(s, q)
+
+
+# ---- element-wise generalised Barrett product (eltwise.cu:FMult): inputs < in_mf*q
+def reduce_from(x, q, k):
+    if k >= 8:
+        x = csub(x, q << 2)
+    if k >= 4:
+        x = csub(x, q << 1)
+    if k >= 2:
+        x = csub(x, q)
+    return x
+
+
+def eltwise_mult(a, b, q, in_mf):
+    x, y = reduce_from(a, q, in_mf), reduce_from(b, q, in_mf)
+    pmu, shift = prod_constants(q)
+    u = x * y
+    lo, hi = u & M64, u >> 64
+    c1 = ((lo >> shift) | (hi << (64 - shift))) & M64 if shift else lo
+    z = (lo - mulhi(c1, pmu) * q) & M64
+    return csub(z, q)
+
+
+# ---- key-switch glue (seal.cu)
+def shoup_lazy(x, w, q):
+    return (x * w - mulhi(x, shoup(w, q)) * q) & M64
+
+
+def ks_mac_finish(acc, q):
+    """ks_mac_kernel's tail: a 128-bit accumulator hi:lo -> [0, q):  hi * (2^64 mod q) + lo, both lazily"""
+    hi, lo = acc >> 64, acc & M64
+    v = (shoup_lazy(hi, (1 << 64) % q, q) + barrett_lazy(lo, q)) & M64
+    assert v < 4 * q
+    return csub(csub(v, q << 1), q)
+
+
+def ks_finish(prod, t_ntt, modswitch, q):
+    """ks_finish_kernel: (prod + 4q - t_ntt) * modswitch mod q for prod < q, t_ntt < 4q"""
+    x = (prod + (q << 2) - t_ntt) & M64
+    x = reduce_from(x, q, 8)
+    return csub(shoup_lazy(x, modswitch, q), q)

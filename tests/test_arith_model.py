@@ -112,3 +112,58 @@ def test_fast_inverse_slot_bounds(K):
         assert len(over) == 4 and worst == 128        # the 4 of 16 slots the pass-boundary fix-up reduces
     # after the fix-up (barrett_lazy3_bigq -> < 3q) every slot is below 8q again: the next pass may start
     assert all(min(b, 3) <= am.K_FAST_BOUND for b in bounds)
+
+
+def test_small_mode_words():
+    rng = random.Random(6)
+    for q in [3, 5, 12289, (1 << 29) + 11, (1 << 30) - 35]:
+        for w in [1, q - 1, q >> 1] + [rng.randrange(1, q) for _ in range(6)]:
+            for x in _operands(1 << 32, rng, 120):
+                r = am.mul_tw32(x, w, q)                      # any 32-bit x -> [0,2q)
+                assert r < 2 * q and (r - x * w) % q == 0
+        for c in [q, 2 * q]:
+            for x in _operands(2 * c, rng, 100):
+                assert am.csub32(x, c) == am.csub(x, c)       # min(x, x - c) with wrap-around == conditional subtraction
+
+
+@pytest.mark.parametrize("r", [30, 46, 61, 62])
+def test_montgomery_reduction(r):
+    rng = random.Random(7)
+    R = 1 << r
+    for q in [3, (1 << (r - 1)) - 1 | 1, R - 1 if (R - 1) % 2 else R - 3] + [rng.randrange(3, R) | 1 for _ in range(6)]:
+        if q >= R or q % 2 == 0:
+            continue
+        Rinv = pow(R, -1, q)
+        for _ in range(300):
+            a, b = rng.randrange(q), rng.randrange(q)
+            t = a * b
+            assert am.redc(t >> 64, t & M64, q, r) == (t * Rinv) % q
+        for t in [0, 1, q - 1, q * R - 1, (q - 1) * (q - 1), R, R - 1]:
+            if t < q * R:
+                assert am.redc(t >> 64, t & M64, q, r) == (t * Rinv) % q
+
+
+@pytest.mark.parametrize("in_mf", [1, 2, 4])
+def test_eltwise_generalised_barrett(in_mf):
+    rng = random.Random(8)
+    qs = [3, 5, 65537, (1 << 40) + 15, (1 << 50) - 27, (1 << 60) - 93, (1 << 61) - 1]
+    if in_mf == 1:
+        qs.append((1 << 62) - 57)
+    for q in qs:
+        assert in_mf * q < (1 << 63)
+        for a in _operands(in_mf * q, rng, 40):
+            for b in _operands(in_mf * q, rng, 40):
+                assert am.eltwise_mult(a, b, q, in_mf) == (a * b) % q
+
+
+def test_key_switch_glue():
+    rng = random.Random(9)
+    for q in [(1 << 32) + 15, (1 << 50) - 27, (1 << 60) - 93, (1 << 61) - 1]:
+        # 64 summands per launch, each (lazy transform output < 4q) x (key word < q): the reference accumulates the
+        # same sums in 128 bits without reduction (key-switch-internal.cpp:93-113)
+        for acc in [0, 1, (1 << 64) - 1, 1 << 64, (1 << 128) - 1] + [rng.randrange(1 << 128) for _ in range(300)]:
+            assert am.ks_mac_finish(acc, q) == acc % q
+        for _ in range(300):
+            prod, t, ms = rng.randrange(q), rng.randrange(4 * q), rng.randrange(q)
+            assert am.ks_finish(prod, t, ms, q) == ((prod - t) * ms) % q
+        assert am.ks_finish(0, 4 * q - 1, q - 1, q) == ((-(4 * q - 1)) * (q - 1)) % q
